@@ -1,0 +1,38 @@
+"""Drop-in for the reference's ``bdcn_new.BDCN`` (bdcn_new.py:65-217) backed by libegn.so.
+
+Same constructor, ``load_state_dict`` key set (182 tensors), ``.cuda()/.eval()``
+and ``__call__(x[B,3,H,W]) -> list`` whose last entry is the fused edge map - the only output the
+reference consumes (utils.py:649, evaluate.py:106).  The ten per-scale sigmoids are dead at
+inference and are returned as ``None`` placeholders."""
+import torch
+
+from ._modules import EngineBound
+from .engine import NET_BDCN
+from .shapes import bdcn_param_shapes
+
+
+class BDCN(EngineBound):
+    _net = NET_BDCN
+
+    def __init__(self, pretrain=None, logger=None, rate=4):
+        super().__init__()
+        if rate != 4:
+            raise ValueError("egn_b200.BDCN supports the reference default rate=4 only")
+        self.pretrain = pretrain
+        self.declare(bdcn_param_shapes(), seed=11)
+        self._init_binding()
+        if pretrain:
+            sd = torch.load(pretrain, map_location="cpu")
+            own = self.state_dict()
+            own.update({k: v for k, v in sd.items() if k in own and "features" in k})
+            self.load_state_dict(own)
+
+    def edge(self, x):
+        """x: [B,1,H,W] grey or [B,3,H,W] -> fused edge map [B,1,H,W] (= reference forward(x)[-1])."""
+        if not x.is_cuda:
+            raise RuntimeError("egn_b200.BDCN runs on CUDA tensors only (no CPU fallback)")
+        return self._ensure_ctx(x.device).bdcn_forward(x)
+
+    def forward(self, x):
+        fuse = self.edge(x)
+        return [None] * 10 + [fuse]

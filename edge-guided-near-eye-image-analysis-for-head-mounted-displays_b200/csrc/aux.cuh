@@ -1,0 +1,504 @@
+// Bandwidth-bound helper kernels of the edge+ESF-Net graph (all split-bf16 NHWC unless noted).
+#pragma once
+#include "common.cuh"
+
+// A channel window of a split buffer.
+struct View {
+  bf16* hi;
+  bf16* lo;
+  int C;      // channels of the underlying buffer
+  int coff;   // first channel of the window
+  int n_off;  // first frame of the window
+};
+
+static inline View make_view(const Act& a, int coff, int n_off = 0) {
+  View v;
+  v.hi = a.hi; v.lo = a.lo; v.C = a.C; v.coff = coff; v.n_off = n_off;
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// First layer: 3x3, pad 1, from up to two fp32 single-channel planes [B][H][W]
+// (vgg16_c.py:11 conv1_1 on cat(img,img,img) with the three input channels pre-summed;
+//  utils.py:1042 convBlock.conv1 of the ESF-Net head, input_concat => two planes).
+struct FirstConvParams {
+  const float* in[3];   // input planes (frame 0); cin of them are used
+  long long fstride[3]; // floats between consecutive frames of each plane
+  int cin;
+  const float* w;       // [cin][9][cout]
+  const float* bias;    // [cout]
+  View dst;
+  int B, H, W, cout, act;
+};
+
+__global__ void first_conv_kernel(const FirstConvParams p) {
+  const int groups = p.cout / 8;
+  const long long total = (long long)p.B * p.H * p.W * groups;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int gidx = (int)(idx % groups);
+  const long long pix = idx / groups;
+  const int x = (int)(pix % p.W);
+  const int y = (int)((pix / p.W) % p.H);
+  const int n = (int)(pix / ((long long)p.W * p.H));
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = __ldg(p.bias + gidx * 8 + i);
+  for (int ci = 0; ci < p.cin; ++ci) {
+    const float* in = p.in[ci] + (size_t)n * p.fstride[ci];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int yy = y + r - 1;
+      if (yy < 0 || yy >= p.H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int xx = x + s - 1;
+        if (xx < 0 || xx >= p.W) continue;
+        const float a = __ldg(in + (size_t)yy * p.W + xx);
+        const float* w = p.w + ((size_t)(ci * 9 + r * 3 + s)) * p.cout + gidx * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(a, __ldg(w + i), acc[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = apply_act(acc[i], p.act);
+  const size_t o = ((size_t)(n + p.dst.n_off) * p.H * p.W + (size_t)y * p.W + x) * p.dst.C + p.dst.coff + gidx * 8;
+  store8(p.dst.hi, p.dst.lo, o, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// Last layer: dec.final.conv2 32->3 3x3 + leaky-relu + eval BatchNorm -> fp32 NCHW logits
+// (utils.py:1046-1050).  One thread per pixel.
+struct LastConvParams {
+  View src;             // 32 channels
+  const float* w;       // [9][32][3]
+  const float* bias;    // [3]
+  const float* scale;   // [3]  BN folded: y = act(conv)*scale + shift
+  const float* shift;
+  float* out;           // [B][3][H][W]
+  int B, H, W;
+};
+
+__global__ void last_conv_kernel(const LastConvParams p) {
+  __shared__ float sw[9 * 32 * 3];
+  for (int i = threadIdx.x; i < 9 * 32 * 3; i += blockDim.x) sw[i] = p.w[i];
+  __syncthreads();
+  const long long total = (long long)p.B * p.H * p.W;
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const int x = (int)(pix % p.W);
+  const int y = (int)((pix / p.W) % p.H);
+  const int n = (int)(pix / ((long long)p.W * p.H));
+  float a0 = p.bias[0], a1 = p.bias[1], a2 = p.bias[2];
+  for (int r = 0; r < 3; ++r) {
+    const int yy = y + r - 1;
+    if (yy < 0 || yy >= p.H) continue;
+    for (int s = 0; s < 3; ++s) {
+      const int xx = x + s - 1;
+      if (xx < 0 || xx >= p.W) continue;
+      const size_t base = ((size_t)(n + p.src.n_off) * p.H * p.W + (size_t)yy * p.W + xx) * p.src.C + p.src.coff;
+      const float* w = sw + (r * 3 + s) * 96;
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        float v[8];
+        load8(p.src.hi, p.src.lo, base + c8 * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float* ww = w + (c8 * 8 + i) * 3;
+          a0 = fmaf(v[i], ww[0], a0);
+          a1 = fmaf(v[i], ww[1], a1);
+          a2 = fmaf(v[i], ww[2], a2);
+        }
+      }
+    }
+  }
+  const size_t hw = (size_t)p.H * p.W;
+  const size_t o = (size_t)n * 3 * hw + (size_t)y * p.W + x;
+  p.out[o] = apply_act(a0, ACT_LRELU) * p.scale[0] + p.shift[0];
+  p.out[o + hw] = apply_act(a1, ACT_LRELU) * p.scale[1] + p.shift[1];
+  p.out[o + 2 * hw] = apply_act(a2, ACT_LRELU) * p.scale[2] + p.shift[2];
+}
+
+// ------------------------------------------------------------------------------------------
+// MaxPool2d(2, stride s, ceil_mode=True) (vgg16_c.py:15,20,27,34).  Copies the winning hi/lo pair.
+struct PoolParams {
+  View src, dst;
+  int B, Hi, Wi, Ho, Wo, stride, Cv;   // Cv: channels pooled (multiple of 8)
+};
+
+__global__ void maxpool_kernel(const PoolParams p) {
+  const int groups = p.Cv / 8;
+  const long long total = (long long)p.B * p.Ho * p.Wo * groups;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int gidx = (int)(idx % groups);
+  const long long pix = idx / groups;
+  const int x = (int)(pix % p.Wo);
+  const int y = (int)((pix / p.Wo) % p.Ho);
+  const int n = (int)(pix / ((long long)p.Wo * p.Ho));
+  BF8 bh, bl;
+  float best[8];
+  bool first = true;
+  for (int r = 0; r < 2; ++r) {
+    const int yy = y * p.stride + r;
+    if (yy >= p.Hi) continue;
+    for (int s = 0; s < 2; ++s) {
+      const int xx = x * p.stride + s;
+      if (xx >= p.Wi) continue;
+      const size_t i = ((size_t)(n + p.src.n_off) * p.Hi * p.Wi + (size_t)yy * p.Wi + xx) * p.src.C + p.src.coff + gidx * 8;
+      const BF8 h = *reinterpret_cast<const BF8*>(p.src.hi + i);
+      const BF8 l = *reinterpret_cast<const BF8*>(p.src.lo + i);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float v = join_bf16(h.v[k], l.v[k]);
+        if (first || v > best[k]) { best[k] = v; bh.v[k] = h.v[k]; bl.v[k] = l.v[k]; }
+      }
+      first = false;
+    }
+  }
+  const size_t o = ((size_t)(n + p.dst.n_off) * p.Ho * p.Wo + (size_t)y * p.Wo + x) * p.dst.C + p.dst.coff + gidx * 8;
+  *reinterpret_cast<BF8*>(p.dst.hi + o) = bh;
+  *reinterpret_cast<BF8*>(p.dst.lo + o) = bl;
+}
+
+// ------------------------------------------------------------------------------------------
+// InstanceNorm2d(affine=False, eps=1e-5, biased variance) (RITnet_v2.py:37,56).
+// Pass 1: per-(frame, channel) sum / sum of squares in double.
+struct StatsParams {
+  View src;
+  double* sums;         // [B][Cv][2], zeroed by the caller
+  int B, HW, Cv, slabs; // Cv multiple of 8
+};
+
+__global__ void instnorm_stats_kernel(const StatsParams p) {
+  extern __shared__ double sh[];          // [Cv][2]
+  const int groups = p.Cv / 8;
+  const int n = blockIdx.y;
+  const int slab = blockIdx.x;
+  for (int i = threadIdx.x; i < p.Cv * 2; i += blockDim.x) sh[i] = 0.0;
+  __syncthreads();
+  const int rows = blockDim.x / groups;                  // pixel lanes per block
+  const int gidx = threadIdx.x % groups;
+  const int row = threadIdx.x / groups;
+  const int per = (p.HW + p.slabs - 1) / p.slabs;
+  const int p0 = slab * per;
+  const int p1 = min(p.HW, p0 + per);
+  if (row < rows) {
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+    for (int px = p0 + row; px < p1; px += rows) {
+      float v[8];
+      load8(p.src.hi, p.src.lo, ((size_t)(n + p.src.n_off) * p.HW + px) * p.src.C + p.src.coff + gidx * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&sh[(gidx * 8 + i) * 2], (double)s[i]);
+      atomicAdd(&sh[(gidx * 8 + i) * 2 + 1], (double)q[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.Cv * 2; i += blockDim.x)
+    atomicAdd(&p.sums[(size_t)n * p.Cv * 2 + i], sh[i]);
+}
+
+// Pass 2: y = act((x - mean) * rstd), optionally followed by AvgPool2d(2) (Transition_down,
+// RITnet_v2.py:40-44; the 1x1 conv that the reference applies before the pool is applied after it
+// by the caller - both are linear, so conv(pool(z)) == pool(conv(z))).
+struct NormApplyParams {
+  View src, dst;
+  const double* sums;   // [B][Cv][2]
+  int B, H, W, Cv, act, pool;
+};
+
+__global__ void instnorm_apply_kernel(const NormApplyParams p) {
+  const int groups = p.Cv / 8;
+  const int Ho = p.pool ? p.H / 2 : p.H, Wo = p.pool ? p.W / 2 : p.W;
+  const long long total = (long long)p.B * Ho * Wo * groups;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int gidx = (int)(idx % groups);
+  const long long pix = idx / groups;
+  const int x = (int)(pix % Wo);
+  const int y = (int)((pix / Wo) % Ho);
+  const int n = (int)(pix / ((long long)Wo * Ho));
+  float mean[8], rstd[8];
+  const double inv = 1.0 / ((double)p.H * p.W);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const double s = p.sums[((size_t)n * p.Cv + gidx * 8 + i) * 2];
+    const double q = p.sums[((size_t)n * p.Cv + gidx * 8 + i) * 2 + 1];
+    const double m = s * inv;
+    double var = q * inv - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[i] = (float)m;
+    rstd[i] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+  float out[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) out[i] = 0.f;
+  const int reps = p.pool ? 2 : 1;
+  for (int r = 0; r < reps; ++r)
+    for (int s = 0; s < reps; ++s) {
+      const int yy = p.pool ? y * 2 + r : y, xx = p.pool ? x * 2 + s : x;
+      float v[8];
+      load8(p.src.hi, p.src.lo, ((size_t)(n + p.src.n_off) * p.H * p.W + (size_t)yy * p.W + xx) * p.src.C + p.src.coff + gidx * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) out[i] += apply_act((v[i] - mean[i]) * rstd[i], p.act);
+    }
+  if (p.pool) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] *= 0.25f;
+  }
+  store8(p.dst.hi, p.dst.lo, ((size_t)(n + p.dst.n_off) * Ho * Wo + (size_t)y * Wo + x) * p.dst.C + p.dst.coff + gidx * 8, out);
+}
+
+// ------------------------------------------------------------------------------------------
+// F.interpolate(bilinear, align_corners=False, scale_factor=2) (RITnet_v2.py:80-83).
+// One thread per (output pixel, channel); `Cs` real channels are written at dst.coff.
+struct UpsampleParams {
+  View src, dst;
+  int B, Hi, Wi, Cs;
+};
+
+__global__ void upsample2x_kernel(const UpsampleParams p) {
+  const int Ho = p.Hi * 2, Wo = p.Wi * 2;
+  const long long total = (long long)p.B * Ho * Wo * p.Cs;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % p.Cs);
+  const long long pix = idx / p.Cs;
+  const int x = (int)(pix % Wo);
+  const int y = (int)((pix / Wo) % Ho);
+  const int n = (int)(pix / ((long long)Wo * Ho));
+  const float sy = fmaxf(0.f, (y + 0.5f) * 0.5f - 0.5f);
+  const float sx = fmaxf(0.f, (x + 0.5f) * 0.5f - 0.5f);
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = min(y0 + 1, p.Hi - 1), x1 = min(x0 + 1, p.Wi - 1);
+  const float ly = sy - y0, lx = sx - x0;
+  const size_t fb = (size_t)(n + p.src.n_off) * p.Hi * p.Wi;
+  auto at = [&](int yy, int xx) {
+    const size_t i = (fb + (size_t)yy * p.Wi + xx) * p.src.C + p.src.coff + c;
+    return join_bf16(p.src.hi[i], p.src.lo[i]);
+  };
+  const float top = (1.f - lx) * at(y0, x0) + lx * at(y0, x1);
+  const float bot = (1.f - lx) * at(y1, x0) + lx * at(y1, x1);
+  const float v = (1.f - ly) * top + ly * bot;
+  bf16 h, l;
+  split_bf16(v, h, l);
+  const size_t o = ((size_t)(n + p.dst.n_off) * Ho * Wo + (size_t)y * Wo + x) * p.dst.C + p.dst.coff + c;
+  p.dst.hi[o] = h;
+  p.dst.lo[o] = l;
+}
+
+// ------------------------------------------------------------------------------------------
+// Spatial mean of a channel window -> fp32 [B][Cs]  (latent, RITnet_v2.py:282).
+__global__ void spatial_mean_kernel(View src, float* out, int B, int HW, int Cs) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
+    float s = 0.f;
+    for (int px = 0; px < HW; ++px) {
+      const size_t i = ((size_t)(n + src.n_off) * HW + px) * src.C + src.coff + c;
+      s += join_bf16(src.hi[i], src.lo[i]);
+    }
+    out[(size_t)n * Cs + c] = s / (float)HW;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// BDCN tail (bdcn_new.py:118-191 collapsed): per full-resolution pixel
+//   fuse = b + sum_k alpha_k * U_k(sA_k + cA_k) + beta_k * U_k(sB_k + cB_k),  edge = sigmoid(fuse)
+// U_1 = identity, U_2..5 = the learnable ConvTranspose2d kernels followed by the crop.
+struct BdcnTailParams {
+  const float* score[5];   // [N][h][w][2]  (A = score_dsn k, B = score_dsn k_1), without biases
+  int h[5], w[5];
+  const float* kern[5];    // [K][K] fp32 (kern[0] unused)
+  int K[5], stride[5], crop[5];
+  float alpha[5], beta[5], cA[5], cB[5], fuse_bias;
+  float* out;              // [N][H][W]
+  int N, H, W;
+};
+
+__global__ void bdcn_tail_kernel(const BdcnTailParams p) {
+  const long long total = (long long)p.N * p.H * p.W;
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const int x = (int)(pix % p.W);
+  const int y = (int)((pix / p.W) % p.H);
+  const int n = (int)(pix / ((long long)p.W * p.H));
+  const float2 s1 = reinterpret_cast<const float2*>(p.score[0])[pix];
+  float acc = p.fuse_bias + p.alpha[0] * (s1.x + p.cA[0]) + p.beta[0] * (s1.y + p.cB[0]);
+#pragma unroll
+  for (int k = 1; k < 5; ++k) {
+    const int st = p.stride[k], K = p.K[k];
+    const int yy = y + p.crop[k], xx = x + p.crop[k];      // coordinate in the uncropped output
+    // out[yy] = sum_i in[i] * kern[yy - i*st],  0 <= yy - i*st < K
+    int i0 = (yy - K + st) / st;  if (yy - K + 1 <= 0) i0 = 0;
+    int j0 = (xx - K + st) / st;  if (xx - K + 1 <= 0) j0 = 0;
+    const int i1 = min(yy / st, p.h[k] - 1), j1 = min(xx / st, p.w[k] - 1);
+    float ua = 0.f, ub = 0.f;
+    for (int i = i0; i <= i1; ++i) {
+      const int ky = yy - i * st;
+      if (ky < 0 || ky >= K) continue;
+      for (int j = j0; j <= j1; ++j) {
+        const int kx = xx - j * st;
+        if (kx < 0 || kx >= K) continue;
+        const float kv = __ldg(p.kern[k] + ky * K + kx);
+        const float2 s = reinterpret_cast<const float2*>(p.score[k])[((size_t)n * p.h[k] + i) * p.w[k] + j];
+        ua = fmaf(kv, s.x + p.cA[k], ua);
+        ub = fmaf(kv, s.y + p.cB[k], ub);
+      }
+    }
+    acc += p.alpha[k] * ua + p.beta[k] * ub;
+  }
+  p.out[pix] = 1.f / (1.f + __expf(-acc));
+}
+
+// ------------------------------------------------------------------------------------------
+// Regression head input: fp32 NHWC [B][15][20][Cf] gathered from the bottleneck windows
+// (image frames, then edge frames when add_edge) with the optional AdaIN transform
+// (RITnet_v2.py:280-308: unbiased variance + 1e-5).
+struct HeadInputParams {
+  View src[2];
+  int nsrc, Cs;            // channels per source (153)
+  const float* adain;      // [B][2][Cf] (gamma, beta) or null
+  float* out;              // [B][HW][Cf]
+  int B, HW;
+};
+
+__global__ void head_input_kernel(const HeadInputParams p) {
+  const int Cf = p.nsrc * p.Cs;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < Cf; c += blockDim.x) {
+    const View& s = p.src[c / p.Cs];
+    const int cc = c % p.Cs;
+    float v[300];
+    float sum = 0.f;
+    for (int px = 0; px < p.HW; ++px) {
+      const size_t i = ((size_t)(n + s.n_off) * p.HW + px) * s.C + s.coff + cc;
+      v[px] = join_bf16(s.hi[i], s.lo[i]);
+      sum += v[px];
+    }
+    float g = 1.f, b = 0.f, mean = 0.f, istd = 1.f;
+    if (p.adain) {
+      mean = sum / p.HW;
+      float q = 0.f;
+      for (int px = 0; px < p.HW; ++px) q += (v[px] - mean) * (v[px] - mean);
+      istd = 1.f / sqrtf(q / (p.HW - 1) + 1e-5f);
+      g = p.adain[((size_t)n * 2 + 0) * Cf + c];
+      b = p.adain[((size_t)n * 2 + 1) * Cf + c];
+    }
+    for (int px = 0; px < p.HW; ++px)
+      p.out[((size_t)n * p.HW + px) * Cf + c] = p.adain ? (v[px] - mean) * istd * g + b : v[px];
+  }
+}
+
+// Generic fp32 NHWC convolution (valid or zero padding, stride s) for the small head layers
+// (utils.py:992-1005) and the AdaIN style encoder (RITnet_v2.py:95-102).  Thread per (pixel, cout).
+struct ConvF32Params {
+  const float* in;    // [B][Hi][Wi][Ci]
+  const float* w;     // [kh][kw][Ci][Co]
+  const float* bias;  // [Co] or null
+  float* out;         // [B][Ho][Wo][Co]
+  int B, Hi, Wi, Ci, Ho, Wo, Co, kh, kw, stride, pad, act, reflect;
+};
+
+__global__ void conv_f32_kernel(const ConvF32Params p) {
+  const long long total = (long long)p.B * p.Ho * p.Wo * p.Co;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int co = (int)(idx % p.Co);
+  const long long pix = idx / p.Co;
+  const int x = (int)(pix % p.Wo);
+  const int y = (int)((pix / p.Wo) % p.Ho);
+  const int n = (int)(pix / ((long long)p.Wo * p.Ho));
+  float acc = p.bias ? p.bias[co] : 0.f;
+  for (int r = 0; r < p.kh; ++r) {
+    int yy = y * p.stride + r - p.pad;
+    if (p.reflect) { if (yy < 0) yy = -yy; if (yy >= p.Hi) yy = 2 * p.Hi - 2 - yy; }
+    if (yy < 0 || yy >= p.Hi) continue;
+    for (int s = 0; s < p.kw; ++s) {
+      int xx = x * p.stride + s - p.pad;
+      if (p.reflect) { if (xx < 0) xx = -xx; if (xx >= p.Wi) xx = 2 * p.Wi - 2 - xx; }
+      if (xx < 0 || xx >= p.Wi) continue;
+      const float* a = p.in + (((size_t)n * p.Hi + yy) * p.Wi + xx) * p.Ci;
+      const float* w = p.w + ((size_t)(r * p.kw + s) * p.Ci) * p.Co + co;
+      for (int ci = 0; ci < p.Ci; ++ci) acc = fmaf(a[ci], w[(size_t)ci * p.Co], acc);
+    }
+  }
+  p.out[idx] = apply_act(acc, p.act);
+}
+
+// AvgPool2d(2) on fp32 NHWC (utils.py:990).
+__global__ void avgpool_f32_kernel(const float* in, float* out, int B, int Hi, int Wi, int C) {
+  const int Ho = Hi / 2, Wo = Wi / 2;
+  const long long total = (long long)B * Ho * Wo * C;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  const long long pix = idx / C;
+  const int x = (int)(pix % Wo);
+  const int y = (int)((pix / Wo) % Ho);
+  const int n = (int)(pix / ((long long)Wo * Ho));
+  const float* b = in + (((size_t)n * Hi + 2 * y) * Wi + 2 * x) * C + c;
+  out[idx] = 0.25f * (b[0] + b[C] + b[(size_t)Wi * C] + b[(size_t)Wi * C + C]);
+}
+
+// Global average pool fp32 NHWC -> [B][C]
+__global__ void gap_f32_kernel(const float* in, float* out, int HW, int C) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int px = 0; px < HW; ++px) s += in[((size_t)n * HW + px) * C + c];
+    out[(size_t)n * C + c] = s / HW;
+  }
+}
+
+// Linear layer fp32: out[b][o] = act(in[b] . w[o] + bias[o]);  act: 0 none, 1 relu, 3 selu,
+// 4 = ellipse head split (tanh on 0:2,5:7; sigmoid on 2:4,7:9; identity on 4,9; utils.py:1023-1036).
+__global__ void linear_kernel(const float* in, const float* w, const float* bias, float* out, int B,
+                              int I, int O, int act) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * O) return;
+  const int o = idx % O, b = idx / O;
+  float acc = bias[o];
+  const float* a = in + (size_t)b * I;
+  const float* ww = w + (size_t)o * I;
+  for (int i = 0; i < I; ++i) acc = fmaf(a[i], ww[i], acc);
+  if (act == 1) acc = fmaxf(acc, 0.f);
+  else if (act == 3) {
+    const float alpha = 1.6732632423543772848170429916717f, scale = 1.0507009873554804934193349852946f;
+    acc = scale * (acc > 0.f ? acc : alpha * (expf(acc) - 1.f));
+  } else if (act == 4) {
+    const int k = o % 5;
+    if (k < 2) acc = tanhf(acc);
+    else if (k < 4) acc = 1.f / (1.f + expf(-acc));
+  }
+  out[idx] = acc;
+}
+
+// softmax over the 3 classes of fp32 NCHW logits -> fp32 NHWC [B][H][W][3] (RITnet_v2.py:290-294)
+__global__ void softmax3_nhwc_kernel(const float* logits, float* out, int B, int HW) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * HW) return;
+  const int n = (int)(idx / HW);
+  const int px = (int)(idx % HW);
+  const float* l = logits + (size_t)n * 3 * HW + px;
+  const float a = l[0], b = l[HW], c = l[2 * (size_t)HW];
+  const float m = fmaxf(a, fmaxf(b, c));
+  const float ea = expf(a - m), eb = expf(b - m), ec = expf(c - m);
+  const float inv = 1.f / (ea + eb + ec);
+  out[idx * 3 + 0] = ea * inv;
+  out[idx * 3 + 1] = eb * inv;
+  out[idx * 3 + 2] = ec * inv;
+}
+
+template <typename K, typename P>
+static void launch_1d(K kernel, const P& p, long long total, cudaStream_t stream, int threads = 256) {
+  const long long blocks = (total + threads - 1) / threads;
+  kernel<<<(unsigned)blocks, threads, 0, stream>>>(p);
+  CUDA_OK(cudaGetLastError());
+}

@@ -1,0 +1,284 @@
+// extern "C" surface of libegn.so (declared in include/egn.h).
+#include "../../include/egn.h"
+
+#include "engine.cuh"
+
+struct egn_ctx {
+  Engine eng;
+  float* partial = nullptr;   // seg-post slice partials
+  int partial_cap = 0;
+  int* counts = nullptr;
+  int counts_cap = 0;
+};
+
+static thread_local std::string g_err;
+
+#define API_BEGIN try {
+#define API_END                                   \
+  }                                               \
+  catch (const std::exception& e) {               \
+    g_err = e.what();                             \
+    return 1;                                     \
+  }                                               \
+  catch (...) {                                   \
+    g_err = "unknown error";                      \
+    return 1;                                     \
+  }                                               \
+  return 0;
+
+extern "C" {
+
+const char* egn_last_error(void) { return g_err.c_str(); }
+int egn_version(void) { return 100; }
+
+int egn_create(int device, const egn_config* cfg, egn_ctx** out) {
+  API_BEGIN
+  EGN_CHECK(out != nullptr && cfg != nullptr, "null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  EGN_CHECK(e == cudaSuccess && ndev > 0, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  EGN_CHECK(device >= 0 && device < ndev, "bad device index");
+  CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  EGN_CHECK(prop.major == 10, "libegn.so is built for sm_100a (B200) only; found sm_" +
+                                  std::to_string(prop.major) + std::to_string(prop.minor));
+  std::unique_ptr<egn_ctx> c(new egn_ctx());
+  c->eng.device = device;
+  c->eng.num_sms = prop.multiProcessorCount;
+  c->eng.cfg.add_edge = cfg->add_edge; c->eng.cfg.add_seg = cfg->add_seg;
+  c->eng.cfg.seg_detach = cfg->seg_detach; c->eng.cfg.input_concat = cfg->input_concat;
+  c->eng.cfg.only_edge = cfg->only_edge; c->eng.cfg.style_dim = cfg->style_dim;
+  const char* impl = getenv("EGN_CONV");
+  c->eng.use_tc = !(impl && std::string(impl) == "simt");
+  const char* ns = getenv("EGN_NSPLIT");
+  c->eng.nsplit = ns ? atoi(ns) : 3;
+  EGN_CHECK(c->eng.nsplit == 1 || c->eng.nsplit == 3, "EGN_NSPLIT must be 1 or 3");
+  c->eng.err_flag = (int*)c->eng.mem_misc.alloc(sizeof(int));
+  *out = c.release();
+  API_END
+}
+
+int egn_destroy(egn_ctx* ctx) {
+  API_BEGIN
+  if (ctx) {
+    cudaSetDevice(ctx->eng.device);
+    cudaDeviceSynchronize();
+    delete ctx;
+  }
+  API_END
+}
+
+int egn_set_weights(egn_ctx* ctx, int net, const void* blob, size_t bytes) {
+  API_BEGIN
+  EGN_CHECK(ctx && blob, "null argument");
+  CUDA_OK(cudaSetDevice(ctx->eng.device));
+  if (net == EGN_NET_BDCN) {
+    EGN_CHECK(!ctx->eng.built_bdcn, "BDCN weights already bound; create a new context to reload");
+    ctx->eng.sd_bdcn = parse_blob(blob, bytes);
+    ctx->eng.has_bdcn = true;
+  } else if (net == EGN_NET_ESF) {
+    EGN_CHECK(!ctx->eng.built_esf, "ESF-Net weights already bound; create a new context to reload");
+    ctx->eng.sd_esf = parse_blob(blob, bytes);
+    ctx->eng.has_esf = true;
+  } else {
+    EGN_CHECK(false, "unknown net id");
+  }
+  API_END
+}
+
+int egn_plan(egn_ctx* ctx, int micro_batch) {
+  API_BEGIN
+  EGN_CHECK(ctx, "null context");
+  EGN_CHECK(micro_batch >= 1 && micro_batch <= 256, "micro_batch must be in [1,256]");
+  EGN_CHECK(!ctx->eng.built_bdcn && !ctx->eng.built_esf, "plan must precede the first forward");
+  ctx->eng.mb = micro_batch;
+  API_END
+}
+
+int egn_bdcn_forward(egn_ctx* ctx, const float* x, int planes, float* edge_out, int batch, void* stream) {
+  API_BEGIN
+  EGN_CHECK(ctx && x && edge_out && batch > 0, "bad argument");
+  EGN_CHECK(planes == 1 || planes == 3, "planes must be 1 (grey, replicated by the caller's cat) or 3");
+  CUDA_OK(cudaSetDevice(ctx->eng.device));
+  ctx->eng.bdcn_forward(x, planes, edge_out, batch, (cudaStream_t)stream);
+  API_END
+}
+
+int egn_esf_forward(egn_ctx* ctx, const float* x, const float* edge, float* logits, float* el_out,
+                    float* latent, int batch, void* stream) {
+  API_BEGIN
+  EGN_CHECK(ctx && x && logits && el_out && latent && batch > 0, "bad argument");
+  CUDA_OK(cudaSetDevice(ctx->eng.device));
+  ctx->eng.esf_forward(x, edge, logits, el_out, latent, batch, (cudaStream_t)stream);
+  API_END
+}
+
+int egn_seg_post(egn_ctx* ctx, const float* logits, const float* el_out, const float* cond,
+                 uint8_t* argmax_u8, float* el_pred, int batch, void* stream) {
+  API_BEGIN
+  EGN_CHECK(ctx && logits && el_out && argmax_u8 && el_pred && batch > 0, "bad argument");
+  CUDA_OK(cudaSetDevice(ctx->eng.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ctx->partial_cap < batch) {
+    ctx->partial = (float*)ctx->eng.mem_misc.alloc((size_t)batch * POST_SLICES * 8 * sizeof(float));
+    ctx->partial_cap = batch;
+  }
+  dim3 grid(POST_SLICES, batch);
+  seg_post_kernel<<<grid, POST_THREADS, 0, st>>>(logits, argmax_u8, ctx->partial, batch);
+  CUDA_OK(cudaGetLastError());
+  seg_post_finish_kernel<<<(batch + 127) / 128, 128, 0, st>>>(ctx->partial, el_out, cond, el_pred, batch);
+  CUDA_OK(cudaGetLastError());
+  ctx->eng.launches += 2;
+  API_END
+}
+
+int egn_metrics_accumulate(egn_ctx* ctx, const uint8_t* argmax_u8, const void* labels, int label_is_i64,
+                           const float* cond, const float* pupil_c, const float* iris_c,
+                           const float* el_out, const float* el_pred, double* acc,
+                           float* iou_by_sample, int batch, void* stream) {
+  API_BEGIN
+  EGN_CHECK(ctx && argmax_u8 && labels && cond && acc && batch > 0, "bad argument");
+  EGN_CHECK((pupil_c == nullptr) == (iris_c == nullptr), "pupil_c and iris_c must be given together");
+  EGN_CHECK(!pupil_c || (el_out && el_pred), "centres need el_out and el_pred");
+  CUDA_OK(cudaSetDevice(ctx->eng.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ctx->counts_cap < batch) {
+    ctx->counts = (int*)ctx->eng.mem_misc.alloc((size_t)batch * 9 * sizeof(int));
+    ctx->counts_cap = batch;
+  }
+  CUDA_OK(cudaMemsetAsync(ctx->counts, 0, (size_t)batch * 9 * sizeof(int), st));
+  dim3 grid(10, batch);
+  seg_counts_kernel<<<grid, 256, 0, st>>>(argmax_u8, (const uint8_t*)labels, label_is_i64 ? 8 : 1, ctx->counts,
+                                          EGN_H * EGN_W);
+  CUDA_OK(cudaGetLastError());
+  metrics_finish_kernel<<<(batch + 127) / 128, 128, 0, st>>>(ctx->counts, cond, pupil_c, iris_c, el_out, el_pred, acc,
+                                                             iou_by_sample, batch);
+  CUDA_OK(cudaGetLastError());
+  ctx->eng.launches += 2;
+  API_END
+}
+
+int egn_ellipse_refine(egn_ctx* ctx, const uint8_t* argmax_u8, const float* ell_norm, double* out,
+                       int refine, int batch, void* stream) {
+  API_BEGIN
+  EGN_CHECK(ctx && argmax_u8 && ell_norm && out && batch > 0, "bad argument");
+  CUDA_OK(cudaSetDevice(ctx->eng.device));
+  dim3 grid(2, batch);
+  ellipse_refine_kernel<<<grid, REFINE_THREADS, 0, (cudaStream_t)stream>>>(argmax_u8, ell_norm, out, refine);
+  CUDA_OK(cudaGetLastError());
+  ctx->eng.launches += 1;
+  API_END
+}
+
+long long egn_launch_count(egn_ctx* ctx) { return ctx ? ctx->eng.launches : -1; }
+
+double egn_flops_per_frame(egn_ctx* ctx, int net) {
+  if (!ctx) return -1;
+  try {
+    return net == EGN_NET_BDCN ? ctx->eng.flops_per_frame_bdcn() : ctx->eng.flops_per_frame_esf();
+  } catch (...) { return -1; }
+}
+
+long long egn_debug_read(egn_ctx* ctx, const char* name, float* out, long long capacity, int frames,
+                         int* dims) {
+  try {
+    if (!ctx || !name) return -1;
+    Engine& e = ctx->eng;
+    cudaSetDevice(e.device);
+    cudaDeviceSynchronize();
+    auto it = e.debug_acts.find(name);
+    if (it != e.debug_acts.end()) {
+      const Act* a = it->second.first;
+      const int coff = it->second.second.first, C = it->second.second.second;
+      const int n = std::min(frames, a->N);
+      if (dims) { dims[0] = C; dims[1] = a->H; dims[2] = a->W; }
+      const long long total = (long long)n * C * a->H * a->W;
+      if (!out) return total;
+      if (capacity < total) return -1;
+      const size_t elems = (size_t)n * a->H * a->W * a->C;
+      std::vector<bf16> hi(elems), lo(elems);
+      cudaMemcpy(hi.data(), a->hi, elems * 2, cudaMemcpyDeviceToHost);
+      cudaMemcpy(lo.data(), a->lo, elems * 2, cudaMemcpyDeviceToHost);
+      for (int f = 0; f < n; ++f)
+        for (int y = 0; y < a->H; ++y)
+          for (int x = 0; x < a->W; ++x)
+            for (int c = 0; c < C; ++c) {
+              const size_t i = (((size_t)f * a->H + y) * a->W + x) * a->C + coff + c;
+              out[(((size_t)f * C + c) * a->H + y) * a->W + x] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
+            }
+      return total;
+    }
+    auto jt = e.debug_f32.find(name);
+    if (jt != e.debug_f32.end()) {
+      const std::vector<int>& d = jt->second.second;     // H, W, C (NHWC fp32)
+      if (dims) { dims[0] = d[2]; dims[1] = d[0]; dims[2] = d[1]; }
+      const long long total = (long long)frames * d[0] * d[1] * d[2];
+      if (!out) return total;
+      if (capacity < total) return -1;
+      std::vector<float> tmp(total);
+      cudaMemcpy(tmp.data(), jt->second.first, total * 4, cudaMemcpyDeviceToHost);
+      for (int f = 0; f < frames; ++f)
+        for (int y = 0; y < d[0]; ++y)
+          for (int x = 0; x < d[1]; ++x)
+            for (int c = 0; c < d[2]; ++c)
+              out[(((size_t)f * d[2] + c) * d[0] + y) * d[1] + x] = tmp[(((size_t)f * d[0] + y) * d[1] + x) * d[2] + c];
+      return total;
+    }
+    g_err = std::string("unknown debug tensor: ") + name;
+    return -1;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return -1;
+  }
+}
+
+int egn_conv_selfcheck(egn_ctx* ctx, const char* layer, int frames, double* max_diff, double* max_ref) {
+  API_BEGIN
+  EGN_CHECK(ctx && layer && max_diff && max_ref, "bad argument");
+  Engine& e = ctx->eng;
+  CUDA_OK(cudaSetDevice(e.device));
+  EGN_CHECK(e.use_tc, "selfcheck needs the tensor-core path (unset EGN_CONV=simt)");
+  auto it = e.conv_index.find(layer);
+  EGN_CHECK(it != e.conv_index.end(), std::string("unknown conv layer: ") + layer);
+  ConvLayer& L = *it->second;
+  const int n = std::min(frames, L.g.batch);
+  const size_t px = (size_t)n * L.g.H * L.g.W;
+  std::vector<float> a, b;
+  auto fetch = [&](std::vector<float>& v) {
+    CUDA_OK(cudaDeviceSynchronize());
+    if (L.e.mode == CONV_STORE) {
+      const size_t elems = px * L.e.out_C;
+      std::vector<bf16> hi(elems), lo(elems);
+      CUDA_OK(cudaMemcpy(hi.data(), L.e.out_hi, elems * 2, cudaMemcpyDeviceToHost));
+      CUDA_OK(cudaMemcpy(lo.data(), L.e.out_lo, elems * 2, cudaMemcpyDeviceToHost));
+      v.resize(px * L.e.cout_store);
+      for (size_t p = 0; p < px; ++p)
+        for (int c = 0; c < L.e.cout_store; ++c) {
+          const size_t i = p * L.e.out_C + L.e.out_coff + c;
+          v[p * L.e.cout_store + c] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
+        }
+    } else {
+      v.resize(px * 2);
+      CUDA_OK(cudaMemcpy(v.data(), L.e.score, px * 2 * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+  };
+  TcParams tp = L.tc;
+  tp.g.batch = n; tp.total_tiles = tp.tiles_x * tp.tiles_y * n * tp.n_blocks; tp.e.score_accum = 0;
+  tc_launch(tp, e.num_sms, 0);
+  fetch(a);
+  SimtParams sp = L.simt;
+  sp.g.batch = n; sp.e.score_accum = 0;
+  simt_launch(sp, 0);
+  fetch(b);
+  double md = 0, mr = 0;
+  for (size_t i = 0; i < a.size(); ++i) {
+    md = std::max(md, (double)fabsf(a[i] - b[i]));
+    mr = std::max(mr, (double)fabsf(b[i]));
+    if (a[i] != a[i]) md = 1e30;
+  }
+  *max_diff = md; *max_ref = mr;
+  API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,909 @@
+// Graph executor for the BDCN edge net + ESF-Net forward (host side of libegn.so).
+//
+// Reference graph: bdcn_new.py:116-191, vgg16_c.py:65-88, models/RITnet_v2.py:261-354,
+// utils.py:1013-1037.  The engine owns every activation buffer (split-bf16 NHWC, see common.cuh),
+// repacks the reference state_dict tensors into tensor-core operands once, and runs the forward
+// in micro-batches so the workspace stays bounded for any caller batch.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "aux.cuh"
+#include "common.cuh"
+#include "conv_simt.cuh"
+#include "conv_tc.cuh"
+#include "post.cuh"
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+typedef std::map<std::string, HostTensor> StateDict;
+
+// Blob layout (little endian), produced by egn_b200.pack.pack_state_dict:
+//   u32 magic 'EGNW', u32 count, then per tensor: u32 name_len, name bytes, u32 ndim,
+//   i64 dims[ndim], f32 data[numel]
+static StateDict parse_blob(const void* blob, size_t bytes) {
+  StateDict sd;
+  const uint8_t* p = (const uint8_t*)blob;
+  const uint8_t* end = p + bytes;
+  auto need = [&](size_t n) { EGN_CHECK((size_t)(end - p) >= n, "weight blob truncated"); };
+  need(8);
+  uint32_t magic, count;
+  memcpy(&magic, p, 4); memcpy(&count, p + 4, 4); p += 8;
+  EGN_CHECK(magic == 0x574e4745u, "weight blob: bad magic");
+  for (uint32_t i = 0; i < count; ++i) {
+    need(4);
+    uint32_t nl; memcpy(&nl, p, 4); p += 4;
+    need(nl + 4);
+    std::string name((const char*)p, nl); p += nl;
+    uint32_t nd; memcpy(&nd, p, 4); p += 4;
+    HostTensor t;
+    need(8 * (size_t)nd);
+    for (uint32_t d = 0; d < nd; ++d) { int64_t v; memcpy(&v, p, 8); p += 8; t.shape.push_back(v); }
+    const int64_t n = t.numel();
+    need(4 * (size_t)n);
+    t.data.resize(n);
+    memcpy(t.data.data(), p, 4 * (size_t)n); p += 4 * (size_t)n;
+    sd[name] = std::move(t);
+  }
+  return sd;
+}
+
+static const HostTensor& sd_get(const StateDict& sd, const std::string& k) {
+  auto it = sd.find(k);
+  EGN_CHECK(it != sd.end(), "missing tensor in state_dict: " + k);
+  return it->second;
+}
+
+// ------------------------------------------------------------------------------------------
+struct DevMem {
+  std::vector<void*> ptrs;
+  size_t total = 0;
+  void* alloc(size_t bytes, bool zero = true) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 16;
+    CUDA_OK(cudaMalloc(&p, bytes));
+    if (zero) CUDA_OK(cudaMemset(p, 0, bytes));
+    ptrs.push_back(p);
+    total += bytes;
+    return p;
+  }
+  template <typename T>
+  T* upload(const std::vector<T>& v) {
+    T* d = (T*)alloc(v.size() * sizeof(T), false);
+    if (!v.empty()) CUDA_OK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+  }
+  void release() {
+    for (void* p : ptrs) cudaFree(p);
+    ptrs.clear();
+    total = 0;
+  }
+};
+
+static inline bf16 host_bf16(float v) { return __float2bfloat16_rn(v); }
+
+struct Piece {       // a run of reference input channels living in a buffer
+  const Act* buf;
+  int buf_c, len, n_off;
+};
+
+struct ConvLayer {
+  std::string name;
+  ConvGeom g{};
+  ConvEpi e{};
+  ConvSrc src[EGN_MAX_SRC]{};
+  int nsrc = 0;
+  const Act* src_act[EGN_MAX_SRC]{};
+  bf16* w_hi = nullptr;
+  bf16* w_lo = nullptr;
+  int cout = 0;
+  TcParams tc{};
+  SimtParams simt{};
+  double flops = 0;      // algorithmic 2*MAC at unpadded sizes, per frame
+};
+
+struct EgnConfig {
+  int add_edge = 0, add_seg = 0, input_concat = 0, only_edge = 0, style_dim = 8, seg_detach = 0;
+};
+
+struct Engine {
+  int device = 0;
+  int num_sms = 148;
+  EgnConfig cfg;
+  int mb = 0;                 // micro-batch (frames)
+  bool use_tc = true;
+  int nsplit = 3;
+  StateDict sd_bdcn, sd_esf;
+  bool has_bdcn = false, has_esf = false, built_bdcn = false, built_esf = false;
+  DevMem mem_bdcn, mem_esf, mem_misc;
+  int* err_flag = nullptr;
+  std::map<std::string, std::pair<const Act*, std::pair<int, int>>> debug_acts;  // name -> (buf,(coff,C))
+  std::map<std::string, std::pair<const float*, std::vector<int>>> debug_f32;
+  std::vector<std::unique_ptr<Act>> acts;
+  std::map<std::string, ConvLayer*> conv_index;
+
+  // ---- BDCN
+  struct {
+    Act *f[13], *pool[4], *o[5];
+    float* score[5];
+    int h[5], w[5];
+    FirstConvParams first;
+    const float *first_w_gray, *first_w_rgb;
+    ConvLayer vgg[13];           // index 0 unused (first_conv)
+    ConvLayer ms_in[13], ms_tail[13];
+    BdcnTailParams tail;
+  } bd;
+
+  // ---- ESF
+  struct Block {
+    Act *buf, *xn, *t, *tdin;
+    int in_c, in_pad, inter, op_c, off_out, off_x, off_x1, off_x22, H, W;
+    double* sums_x;
+    double* sums_skip;
+    ConvLayer conv1, conv21, conv22, conv31, conv32, td;
+  };
+  struct UpBlock {
+    Act *buf, *t, *out;
+    int in_c, in_pad, out_c, out_pad, skip_c, H, W;
+    ConvLayer c11, c12, c21, c22;
+  };
+  struct {
+    int E = 0;                    // encoder frames per micro-batch
+    Act *h1, *bt, *fin;
+    FirstConvParams first;
+    ConvLayer head2, final1;
+    Block blk[5];
+    UpBlock up[4];
+    LastConvParams last;
+    // regression head + AdaIN (fp32)
+    int Cf = 0;
+    float *hin, *c1o, *p1o, *c2o, *c3o, *l1o;
+    float *w_c1, *b_c1, *w_c2, *b_c2, *w_c3, *w_l1, *b_l1, *w_l2, *b_l2;
+    float *sm, *se[5], *gap, *sty, *m1, *m2, *adain;
+    float *w_se[5], *b_se[5], *w_se6, *b_se6, *w_m[3], *b_m[3];
+    float* logits_tmp;
+  } es;
+
+  ~Engine() {
+    mem_bdcn.release(); mem_esf.release(); mem_misc.release();
+  }
+
+  Act* new_act(DevMem& mem, int N, int H, int W, int C) {
+    EGN_CHECK(C % 8 == 0, "Act channels must be a multiple of 8");
+    std::unique_ptr<Act> a(new Act());
+    a->N = N; a->H = H; a->W = W; a->C = C;
+    const size_t bytes = a->plane_elems() * sizeof(bf16);
+    a->hi = (bf16*)mem.alloc(bytes);
+    a->lo = (bf16*)mem.alloc(bytes);
+    acts.push_back(std::move(a));
+    return acts.back().get();
+  }
+
+  // ---------------------------------------------------------------------------------------
+  // Packs a reference conv weight [cout][cin][kh][kw] for the (pieces -> K chunk) layout.
+  // extra groups (MSBlock tail) are packed by passing several weights with their own dilation.
+  struct PackSpec {
+    const float* w; const float* bias; int dil, pad;
+  };
+
+  void build_conv(ConvLayer& L, DevMem& mem, const std::string& name, const std::vector<Piece>& pieces,
+                  const std::vector<PackSpec>& specs, int cout, int cin, int kh, int kw, int H, int W,
+                  int batch) {
+    L.name = name;
+    L.cout = cout;
+    ConvGeom& g = L.g;
+    g.H = H; g.W = W; g.batch = batch;
+    g.groups = (int)specs.size();
+    g.ntaps = kh * kw * g.groups;
+    EGN_CHECK(g.ntaps <= EGN_MAX_TAPS, name + ": too many taps");
+    g.cout_pad = round_up(cout, 16);
+    // ---- views / chunks
+    struct ViewSpan { const Act* buf; int n_off, c_lo, c_hi, first_chunk, src; };
+    std::vector<ViewSpan> views;
+    std::vector<int> piece_view(pieces.size());
+    int ref_total = 0;
+    for (size_t i = 0; i < pieces.size(); ++i) {
+      const Piece& pc = pieces[i];
+      ref_total += pc.len;
+      if (!views.empty() && views.back().buf == pc.buf && views.back().n_off == pc.n_off &&
+          pc.buf_c >= views.back().c_lo) {
+        views.back().c_hi = std::max(views.back().c_hi, pc.buf_c + pc.len);
+      } else {
+        views.push_back({pc.buf, pc.n_off, pc.buf_c, pc.buf_c + pc.len, 0, 0});
+      }
+      piece_view[i] = (int)views.size() - 1;
+    }
+    EGN_CHECK(ref_total == cin, name + ": pieces do not cover cin");
+    L.nsrc = 0;
+    int nch = 0;
+    for (auto& v : views) {
+      int s = -1;
+      for (int k = 0; k < L.nsrc; ++k) if (L.src_act[k] == v.buf) s = k;
+      if (s < 0) {
+        EGN_CHECK(L.nsrc < EGN_MAX_SRC, name + ": too many source buffers");
+        s = L.nsrc++;
+        L.src_act[s] = v.buf;
+        L.src[s].hi = v.buf->hi; L.src[s].lo = v.buf->lo; L.src[s].C = v.buf->C; L.src[s].N = v.buf->N;
+      }
+      v.src = s;
+      v.first_chunk = nch;
+      const int n = ceil_div(v.c_hi - v.c_lo, EGN_KC);
+      for (int k = 0; k < n; ++k) {
+        EGN_CHECK(nch < EGN_MAX_CHUNKS, name + ": too many K chunks");
+        g.chunk_src[nch] = (uint8_t)s;
+        g.chunk_c0[nch] = (int16_t)(v.c_lo + k * EGN_KC);
+        g.chunk_noff[nch] = v.n_off;
+        ++nch;
+      }
+    }
+    g.nchunks = nch;
+    g.kpad = nch * EGN_KC;
+    // ---- taps
+    int t = 0;
+    for (int gi = 0; gi < g.groups; ++gi)
+      for (int r = 0; r < kh; ++r)
+        for (int s = 0; s < kw; ++s, ++t) {
+          g.tap_dy[t] = (int8_t)(r * specs[gi].dil - specs[gi].pad);
+          g.tap_dx[t] = (int8_t)(s * specs[gi].dil - specs[gi].pad);
+          g.tap_grp[t] = (int8_t)gi;
+        }
+    // ---- weights
+    const size_t wn = (size_t)g.ntaps * g.cout_pad * g.kpad;
+    std::vector<bf16> whi(wn, host_bf16(0.f)), wlo(wn, host_bf16(0.f));
+    std::vector<float> bias((size_t)g.groups * g.cout_pad, 0.f);
+    for (int gi = 0; gi < g.groups; ++gi) {
+      int ref_c = 0;
+      for (size_t i = 0; i < pieces.size(); ++i) {
+        const Piece& pc = pieces[i];
+        const ViewSpan& v = views[piece_view[i]];
+        for (int j = 0; j < pc.len; ++j, ++ref_c) {
+          const int rel = pc.buf_c - v.c_lo + j;
+          const int kidx = (v.first_chunk + rel / EGN_KC) * EGN_KC + rel % EGN_KC;
+          for (int co = 0; co < cout; ++co)
+            for (int r = 0; r < kh; ++r)
+              for (int s = 0; s < kw; ++s) {
+                const float wv = specs[gi].w[(((size_t)co * cin + ref_c) * kh + r) * kw + s];
+                const size_t o = ((size_t)(gi * kh * kw + r * kw + s) * g.cout_pad + co) * g.kpad + kidx;
+                const bf16 h = host_bf16(wv);
+                whi[o] = h;
+                wlo[o] = host_bf16(wv - __bfloat162float(h));
+              }
+        }
+      }
+      if (specs[gi].bias)
+        for (int co = 0; co < cout; ++co) bias[(size_t)gi * g.cout_pad + co] = specs[gi].bias[co];
+    }
+    L.w_hi = mem.upload(whi);
+    L.w_lo = mem.upload(wlo);
+    L.e.bias = mem.upload(bias);
+    L.flops = 2.0 * cout * cin * kh * kw * g.groups * H * W;
+  }
+
+  void set_store_epilogue(ConvLayer& L, const Act* dst, int coff, int act, const float* post_scale = nullptr,
+                          const float* post_shift = nullptr) {
+    L.e.mode = CONV_STORE;
+    L.e.act = act;
+    L.e.cout_store = round_up(L.cout, 8);
+    L.e.out_hi = dst->hi; L.e.out_lo = dst->lo; L.e.out_C = dst->C; L.e.out_coff = coff;
+    L.e.post_scale = post_scale; L.e.post_shift = post_shift;
+    EGN_CHECK(dst->H == L.g.H && dst->W == L.g.W, L.name + ": destination size mismatch");
+    EGN_CHECK(coff % 8 == 0 && coff + L.e.cout_store <= dst->C, L.name + ": destination channel window");
+  }
+
+  void finalize_conv(ConvLayer& L) {
+    conv_index[L.name] = &L;
+    // SIMT companion
+    L.simt.g = L.g; L.simt.e = L.e; L.simt.nsplit = nsplit;
+    L.simt.w_hi = L.w_hi; L.simt.w_lo = L.w_lo;
+    for (int s = 0; s < EGN_MAX_SRC; ++s) L.simt.src[s] = L.src[s];
+    // tensor-core parameters
+    L.tc.g = L.g; L.tc.e = L.e; L.tc.err_flag = err_flag;
+    if (use_tc) {
+      tc_configure(L.tc, L.g.cout_pad, nsplit);
+      for (int s = 0; s < L.nsrc; ++s) {
+        const Act* a = L.src_act[s];
+        make_act_map(&L.tc.a_map[0][s], a->hi, a->N, a->H, a->W, a->C);
+        make_act_map(&L.tc.a_map[1][s], a->lo, a->N, a->H, a->W, a->C);
+      }
+      for (int s = L.nsrc; s < EGN_MAX_SRC; ++s) {
+        L.tc.a_map[0][s] = L.tc.a_map[0][0];
+        L.tc.a_map[1][s] = L.tc.a_map[1][0];
+      }
+      make_w_map(&L.tc.w_map[0], L.w_hi, L.g.ntaps * L.g.cout_pad, L.g.kpad, L.tc.n_tile);
+      make_w_map(&L.tc.w_map[1], L.w_lo, L.g.ntaps * L.g.cout_pad, L.g.kpad, L.tc.n_tile);
+    }
+  }
+
+  void run_conv(ConvLayer& L, int batch, cudaStream_t st) {
+    if (use_tc) {
+      TcParams p = L.tc;
+      p.g.batch = batch;
+      p.total_tiles = p.tiles_x * p.tiles_y * batch * p.n_blocks;
+      tc_launch(p, num_sms, st);
+      ++launches;
+    } else {
+      SimtParams p = L.simt;
+      p.g.batch = batch;
+      simt_launch(p, st);
+      ++launches;
+    }
+  }
+
+  long long launches = 0;
+
+  // ======================================================================================= BDCN
+  void build_bdcn() {
+    EGN_CHECK(has_bdcn, "BDCN weights not set");
+    EGN_CHECK(mb > 0, "egn_plan must be called before the first forward");
+    const StateDict& sd = sd_bdcn;
+    DevMem& mem = mem_bdcn;
+    static const char* names[13] = {"conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", "conv3_3",
+                                    "conv4_1", "conv4_2", "conv4_3", "conv5_1", "conv5_2", "conv5_3"};
+    static const int cin[13] = {3, 64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512};
+    static const int cout[13] = {64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512};
+    static const int stage_of[13] = {0, 0, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4};
+    const int sh[5] = {240, 120, 60, 30, 29}, sw_[5] = {320, 160, 80, 40, 39};
+    for (int i = 0; i < 13; ++i) {
+      const int s = stage_of[i];
+      bd.f[i] = new_act(mem, mb, sh[s], sw_[s], cout[i]);
+      debug_acts[std::string("features.") + names[i]] = {bd.f[i], {0, cout[i]}};
+    }
+    const int pc[4] = {64, 128, 256, 512};
+    for (int i = 0; i < 4; ++i) bd.pool[i] = new_act(mem, mb, sh[i + 1], sw_[i + 1], pc[i]);
+    for (int s = 0; s < 5; ++s) {
+      bd.o[s] = new_act(mem, mb, sh[s], sw_[s], 32);
+      bd.h[s] = sh[s]; bd.w[s] = sw_[s];
+      bd.score[s] = (float*)mem.alloc((size_t)mb * sh[s] * sw_[s] * 2 * sizeof(float));
+      debug_f32["score" + std::to_string(s + 1)] = {bd.score[s], {sh[s], sw_[s], 2}};
+    }
+    // conv1_1 on cat(img,img,img): sum the three input-channel slices (utils.py:649)
+    {
+      const HostTensor& w = sd_get(sd, "features.conv1_1.weight");
+      const HostTensor& b = sd_get(sd, "features.conv1_1.bias");
+      std::vector<float> wp(9 * 64);
+      for (int co = 0; co < 64; ++co)
+        for (int t = 0; t < 9; ++t) {
+          double s = 0;
+          for (int ci = 0; ci < 3; ++ci) s += w.data[((size_t)co * 3 + ci) * 9 + t];
+          wp[(size_t)t * 64 + co] = (float)s;
+        }
+      std::vector<float> w3(3 * 9 * 64);
+      for (int co = 0; co < 64; ++co)
+        for (int ci = 0; ci < 3; ++ci)
+          for (int t = 0; t < 9; ++t) w3[((size_t)ci * 9 + t) * 64 + co] = w.data[((size_t)co * 3 + ci) * 9 + t];
+      bd.first_w_gray = mem.upload(wp);
+      bd.first_w_rgb = mem.upload(w3);
+      bd.first.w = bd.first_w_gray;
+      bd.first.bias = mem.upload(b.data);
+      bd.first.dst = make_view(*bd.f[0], 0);
+      bd.first.H = 240; bd.first.W = 320; bd.first.cout = 64; bd.first.act = ACT_RELU;
+    }
+    for (int i = 1; i < 13; ++i) {
+      const int s = stage_of[i];
+      const bool after_pool = (i == 2 || i == 4 || i == 7 || i == 10);
+      const Act* in = after_pool ? bd.pool[s - 1] : bd.f[i - 1];
+      const int dil = s == 4 ? 2 : 1;
+      const HostTensor& w = sd_get(sd, std::string("features.") + names[i] + ".weight");
+      const HostTensor& b = sd_get(sd, std::string("features.") + names[i] + ".bias");
+      build_conv(bd.vgg[i], mem, std::string("features.") + names[i], {{in, 0, cin[i], 0}},
+                 {{w.data.data(), b.data.data(), dil, dil}}, cout[i], cin[i], 3, 3, sh[s], sw_[s], mb);
+      set_store_epilogue(bd.vgg[i], bd.f[i], 0, ACT_RELU);
+      finalize_conv(bd.vgg[i]);
+    }
+    // MSBlocks + collapsed side chain
+    static const int nblk[5] = {2, 2, 3, 3, 3};
+    const HostTensor& fw = sd_get(sd, "fuse.weight");
+    const HostTensor& fb = sd_get(sd, "fuse.bias");
+    int fi = 0;
+    for (int s = 0; s < 5; ++s) {
+      const std::string S = std::to_string(s + 1);
+      const HostTensor& wsA = sd_get(sd, "score_dsn" + S + ".weight");
+      const HostTensor& bsA = sd_get(sd, "score_dsn" + S + ".bias");
+      const HostTensor& wsB = sd_get(sd, "score_dsn" + S + "_1.weight");
+      const HostTensor& bsB = sd_get(sd, "score_dsn" + S + "_1.bias");
+      double cA = bsA.data[0], cB = bsB.data[0];
+      for (int j = 0; j < nblk[s]; ++j, ++fi) {
+        const std::string J = std::to_string(j + 1);
+        const std::string mp = "msblock" + S + "_" + J;
+        const HostTensor& w0 = sd_get(sd, mp + ".conv.weight");
+        const HostTensor& b0 = sd_get(sd, mp + ".conv.bias");
+        ConvLayer& Lin = bd.ms_in[fi];
+        build_conv(Lin, mem, mp + ".conv", {{bd.f[fi], 0, cout[fi], 0}}, {{w0.data.data(), b0.data.data(), 1, 1}},
+                   32, cout[fi], 3, 3, sh[s], sw_[s], mb);
+        set_store_epilogue(Lin, bd.o[s], 0, ACT_RELU);
+        finalize_conv(Lin);
+        ConvLayer& Lt = bd.ms_tail[fi];
+        std::vector<PackSpec> specs;
+        for (int d = 1; d <= 3; ++d) {
+          const HostTensor& wd = sd_get(sd, mp + ".conv" + std::to_string(d) + ".weight");
+          const HostTensor& bdv = sd_get(sd, mp + ".conv" + std::to_string(d) + ".bias");
+          specs.push_back({wd.data.data(), bdv.data.data(), 4 * d, 4 * d});
+        }
+        build_conv(Lt, mem, mp + ".tail", {{bd.o[s], 0, 32, 0}}, specs, 32, 32, 3, 3, sh[s], sw_[s], mb);
+        // collapsed conv{s}_{j}_down -> score_dsn{s}, score_dsn{s}_1 (both linear)
+        const HostTensor& wd = sd_get(sd, "conv" + S + "_" + J + "_down.weight");   // [21][32]
+        const HostTensor& bdn = sd_get(sd, "conv" + S + "_" + J + "_down.bias");
+        std::vector<float> swv(64);
+        for (int c = 0; c < 32; ++c) {
+          double a = 0, b = 0;
+          for (int m = 0; m < 21; ++m) {
+            a += (double)wsA.data[m] * wd.data[(size_t)m * 32 + c];
+            b += (double)wsB.data[m] * wd.data[(size_t)m * 32 + c];
+          }
+          swv[c] = (float)a; swv[32 + c] = (float)b;
+        }
+        for (int m = 0; m < 21; ++m) { cA += (double)wsA.data[m] * bdn.data[m]; cB += (double)wsB.data[m] * bdn.data[m]; }
+        Lt.e.mode = CONV_MSBLOCK;
+        Lt.e.act = ACT_RELU;
+        Lt.e.cout_store = 32;
+        Lt.e.o_hi = bd.o[s]->hi; Lt.e.o_lo = bd.o[s]->lo;
+        Lt.e.score_w = mem.upload(swv);
+        Lt.e.score = bd.score[s];
+        Lt.e.score_accum = j > 0;
+        Lt.flops += 2.0 * 32 * 21 * sh[s] * sw_[s];      // conv_down (the reference's 1x1)
+        finalize_conv(Lt);
+      }
+      bd.tail.cA[s] = (float)cA; bd.tail.cB[s] = (float)cB;
+      double al = 0, be = 0;
+      for (int j = s; j < 5; ++j) al += fw.data[j];          // s_k appears in p_j_1 for j >= k
+      for (int j = 0; j <= s; ++j) be += fw.data[5 + j];     // s_k1 appears in p_j_2 for j <= k
+      bd.tail.alpha[s] = (float)al; bd.tail.beta[s] = (float)be;
+      bd.tail.score[s] = bd.score[s];
+      bd.tail.h[s] = sh[s]; bd.tail.w[s] = sw_[s];
+    }
+    static const char* upn[5] = {"", "upsample_2", "upsample_4", "upsample_8", "upsample_8_5"};
+    static const int upk[5] = {0, 4, 8, 16, 16}, ups[5] = {1, 2, 4, 8, 8}, upc[5] = {0, 1, 2, 4, 0};
+    bd.tail.kern[0] = nullptr; bd.tail.K[0] = 0; bd.tail.stride[0] = 1; bd.tail.crop[0] = 0;
+    for (int s = 1; s < 5; ++s) {
+      const HostTensor& k = sd_get(sd, std::string(upn[s]) + ".weight");
+      EGN_CHECK(k.numel() == upk[s] * upk[s], "upsample kernel size");
+      bd.tail.kern[s] = mem.upload(k.data);
+      bd.tail.K[s] = upk[s]; bd.tail.stride[s] = ups[s]; bd.tail.crop[s] = upc[s];
+    }
+    bd.tail.fuse_bias = fb.data[0];
+    bd.tail.H = 240; bd.tail.W = 320;
+    built_bdcn = true;
+  }
+
+  void maxpool(const Act* src, const Act* dst, int stride, int batch, cudaStream_t st) {
+    PoolParams p;
+    p.src = make_view(*src, 0); p.dst = make_view(*dst, 0);
+    p.B = batch; p.Hi = src->H; p.Wi = src->W; p.Ho = dst->H; p.Wo = dst->W; p.stride = stride; p.Cv = src->C;
+    launch_1d(maxpool_kernel, p, (long long)batch * p.Ho * p.Wo * (p.Cv / 8), st);
+    ++launches;
+  }
+
+  // x: device fp32 [B][planes][H][W]; planes == 1 is the grey frame the reference replicates with
+  // cat(img,img,img) (utils.py:649; conv1_1 then uses input-channel-summed weights), planes == 3 is
+  // the general BDCN.forward input.  edge_out: [B][H][W].
+  void bdcn_forward(const float* x, int planes, float* edge_out, int B, cudaStream_t st) {
+    if (!built_bdcn) build_bdcn();
+    const size_t hw = (size_t)EGN_H * EGN_W;
+    for (int b0 = 0; b0 < B; b0 += mb) {
+      const int nb = std::min(mb, B - b0);
+      FirstConvParams fp = bd.first;
+      fp.B = nb; fp.cin = planes;
+      fp.w = planes == 1 ? bd.first_w_gray : bd.first_w_rgb;
+      for (int c = 0; c < planes; ++c) { fp.in[c] = x + ((size_t)b0 * planes + c) * hw; fp.fstride[c] = (long long)planes * hw; }
+      launch_1d(first_conv_kernel, fp, (long long)nb * hw * 8, st); ++launches;
+      static const int pool_after[13] = {-1, 0, -1, 1, -1, -1, 2, -1, -1, 3, -1, -1, -1};
+      for (int i = 0; i < 13; ++i) {
+        if (i > 0) run_conv(bd.vgg[i], nb, st);
+        run_conv(bd.ms_in[i], nb, st);
+        run_conv(bd.ms_tail[i], nb, st);
+        if (pool_after[i] >= 0) maxpool(bd.f[i], bd.pool[pool_after[i]], pool_after[i] == 3 ? 1 : 2, nb, st);
+      }
+      BdcnTailParams tp = bd.tail;
+      tp.N = nb; tp.out = edge_out + b0 * hw;
+      launch_1d(bdcn_tail_kernel, tp, (long long)nb * hw, st); ++launches;
+    }
+  }
+
+  // ======================================================================================= ESF
+  static std::vector<float> bn_scale(const StateDict& sd, const std::string& p, int c, int pad, std::vector<float>& shift) {
+    const HostTensor& w = sd_get(sd, p + ".weight");
+    const HostTensor& b = sd_get(sd, p + ".bias");
+    const HostTensor& m = sd_get(sd, p + ".running_mean");
+    const HostTensor& v = sd_get(sd, p + ".running_var");
+    std::vector<float> scale(pad, 0.f);
+    shift.assign(pad, 0.f);
+    for (int i = 0; i < c; ++i) {
+      const double s = (double)w.data[i] / std::sqrt((double)v.data[i] + 1e-5);
+      scale[i] = (float)s;
+      shift[i] = (float)((double)b.data[i] - (double)m.data[i] * s);
+    }
+    return scale;
+  }
+
+  // fp32 conv weights [co][ci][kh][kw] -> [kh][kw][ci][co]
+  float* upload_hwio(DevMem& mem, const HostTensor& w) {
+    const int co = (int)w.shape[0], ci = (int)w.shape[1], kh = (int)w.shape[2], kw = (int)w.shape[3];
+    std::vector<float> o((size_t)co * ci * kh * kw);
+    for (int a = 0; a < co; ++a)
+      for (int b = 0; b < ci; ++b)
+        for (int r = 0; r < kh; ++r)
+          for (int s = 0; s < kw; ++s)
+            o[(((size_t)r * kw + s) * ci + b) * co + a] = w.data[(((size_t)a * ci + b) * kh + r) * kw + s];
+    return mem.upload(o);
+  }
+
+  void build_esf() {
+    EGN_CHECK(has_esf, "ESF-Net weights not set");
+    EGN_CHECK(mb > 0, "egn_plan must be called before the first forward");
+    EGN_CHECK(cfg.input_concat + cfg.add_edge < 2, "edge can use only 1 time!");   // RITnet_v2.py:273
+    const StateDict& sd = sd_esf;
+    DevMem& mem = mem_esf;
+    const int E = mb * (cfg.add_edge ? 2 : 1);
+    es.E = E;
+    const int inter[5] = {32, 64, 96, 128, 128}, in_c[5] = {32, 38, 76, 115, 153}, op_c[5] = {38, 76, 115, 153, 153};
+    const int bh[5] = {240, 120, 60, 30, 15}, bw[5] = {320, 160, 80, 40, 20};
+    static const char* bname[5] = {"enc.down_block1", "enc.down_block2", "enc.down_block3", "enc.down_block4", "enc.bottleneck"};
+    es.h1 = new_act(mem, E, 240, 320, 32);
+    es.bt = new_act(mem, E, 15, 20, 160);
+    debug_acts["bt"] = {es.bt, {0, 153}};
+    for (int i = 0; i < 5; ++i) {
+      Block& b = es.blk[i];
+      b.in_c = in_c[i]; b.in_pad = round_up(in_c[i], 8); b.inter = inter[i]; b.op_c = op_c[i];
+      b.H = bh[i]; b.W = bw[i];
+      b.off_out = 0; b.off_x = inter[i]; b.off_x1 = b.off_x + b.in_pad; b.off_x22 = b.off_x1 + inter[i];
+      b.buf = new_act(mem, E, b.H, b.W, b.off_x22 + inter[i]);
+      b.xn = new_act(mem, E, b.H, b.W, b.in_pad);
+      b.t = new_act(mem, E, b.H, b.W, inter[i]);
+      const bool pool = i < 4;
+      b.tdin = new_act(mem, E, pool ? b.H / 2 : b.H, pool ? b.W / 2 : b.W, inter[i] + b.in_pad);
+      b.sums_x = (double*)mem.alloc((size_t)E * b.in_pad * 2 * sizeof(double));
+      b.sums_skip = (double*)mem.alloc((size_t)E * (inter[i] + b.in_pad) * 2 * sizeof(double));
+      const std::string P = bname[i];
+      debug_acts[P + ".x"] = {b.buf, {b.off_x, b.in_c}};
+      debug_acts[P + ".x1"] = {b.buf, {b.off_x1, b.inter}};
+      debug_acts[P + ".x22"] = {b.buf, {b.off_x22, b.inter}};
+      debug_acts[P + ".out"] = {b.buf, {b.off_out, b.inter}};
+    }
+    // head: conv1 (SIMT first layer) -> h1; conv2 + lrelu + BN -> block1.x   (utils.py:1046-1050)
+    {
+      const HostTensor& w = sd_get(sd, "enc.head.conv1.weight");
+      const HostTensor& b = sd_get(sd, "enc.head.conv1.bias");
+      const int ci = (int)w.shape[1];
+      EGN_CHECK(ci == (cfg.input_concat ? 2 : 1), "enc.head.conv1 input channels do not match the setting");
+      std::vector<float> wp((size_t)ci * 9 * 32);
+      for (int co = 0; co < 32; ++co)
+        for (int c = 0; c < ci; ++c)
+          for (int t = 0; t < 9; ++t) wp[((size_t)c * 9 + t) * 32 + co] = w.data[((size_t)co * ci + c) * 9 + t];
+      es.first.w = mem.upload(wp);
+      es.first.bias = mem.upload(b.data);
+      es.first.H = 240; es.first.W = 320; es.first.cout = 32; es.first.act = ACT_LRELU;
+      const HostTensor& w2 = sd_get(sd, "enc.head.conv2.weight");
+      const HostTensor& b2 = sd_get(sd, "enc.head.conv2.bias");
+      build_conv(es.head2, mem, "enc.head.conv2", {{es.h1, 0, 32, 0}}, {{w2.data.data(), b2.data.data(), 1, 1}}, 32, 32,
+                 3, 3, 240, 320, E);
+      std::vector<float> shift;
+      std::vector<float> scale = bn_scale(sd, "enc.head.bn", 32, es.head2.g.cout_pad, shift);
+      set_store_epilogue(es.head2, es.blk[0].buf, es.blk[0].off_x, ACT_LRELU, mem.upload(scale), mem.upload(shift));
+      finalize_conv(es.head2);
+    }
+    for (int i = 0; i < 5; ++i) {
+      Block& b = es.blk[i];
+      const std::string P = bname[i];
+      auto W = [&](const std::string& n) -> const HostTensor& { return sd_get(sd, P + "." + n + ".weight"); };
+      auto Bv = [&](const std::string& n) -> const HostTensor& { return sd_get(sd, P + "." + n + ".bias"); };
+      // conv1 on IN(x)                                          RITnet_v2.py:60
+      build_conv(b.conv1, mem, P + ".conv1", {{b.xn, 0, b.in_c, 0}}, {{W("conv1").data.data(), Bv("conv1").data.data(), 1, 1}},
+                 b.inter, b.in_c, 3, 3, b.H, b.W, E);
+      set_store_epilogue(b.conv1, b.buf, b.off_x1, ACT_LRELU);
+      finalize_conv(b.conv1);
+      // conv21 (1x1) on [x, x1] -> t ; conv22 3x3 -> x22         RITnet_v2.py:61-62
+      build_conv(b.conv21, mem, P + ".conv21", {{b.buf, b.off_x, b.in_c, 0}, {b.buf, b.off_x1, b.inter, 0}},
+                 {{W("conv21").data.data(), Bv("conv21").data.data(), 1, 0}}, b.inter, b.in_c + b.inter, 1, 1, b.H, b.W, E);
+      set_store_epilogue(b.conv21, b.t, 0, ACT_NONE);
+      finalize_conv(b.conv21);
+      build_conv(b.conv22, mem, P + ".conv22", {{b.t, 0, b.inter, 0}}, {{W("conv22").data.data(), Bv("conv22").data.data(), 1, 1}},
+                 b.inter, b.inter, 3, 3, b.H, b.W, E);
+      set_store_epilogue(b.conv22, b.buf, b.off_x22, ACT_LRELU);
+      finalize_conv(b.conv22);
+      // conv31 on [x, x1, x22] -> t ; conv32 -> out             RITnet_v2.py:63-64
+      build_conv(b.conv31, mem, P + ".conv31",
+                 {{b.buf, b.off_x, b.in_c, 0}, {b.buf, b.off_x1, b.inter, 0}, {b.buf, b.off_x22, b.inter, 0}},
+                 {{W("conv31").data.data(), Bv("conv31").data.data(), 1, 0}}, b.inter, b.in_c + 2 * b.inter, 1, 1, b.H, b.W, E);
+      set_store_epilogue(b.conv31, b.t, 0, ACT_NONE);
+      finalize_conv(b.conv31);
+      build_conv(b.conv32, mem, P + ".conv32", {{b.t, 0, b.inter, 0}}, {{W("conv32").data.data(), Bv("conv32").data.data(), 1, 1}},
+                 b.inter, b.inter, 3, 3, b.H, b.W, E);
+      set_store_epilogue(b.conv32, b.buf, b.off_out, ACT_LRELU);
+      finalize_conv(b.conv32);
+      // TD: IN -> lrelu -> (pool) -> 1x1 conv on skip = [out, x]   RITnet_v2.py:40-44,65-66
+      const Act* dst = i < 4 ? es.blk[i + 1].buf : es.bt;
+      const int dst_off = i < 4 ? es.blk[i + 1].off_x : 0;
+      build_conv(b.td, mem, P + ".TD.conv", {{b.tdin, 0, b.inter, 0}, {b.tdin, b.inter, b.in_c, 0}},
+                 {{W("TD.conv").data.data(), Bv("TD.conv").data.data(), 1, 0}}, b.op_c, b.inter + b.in_c, 1, 1,
+                 b.tdin->H, b.tdin->W, E);
+      set_store_epilogue(b.td, dst, dst_off, ACT_NONE);
+      finalize_conv(b.td);
+    }
+    // decoder
+    const int d_in[4] = {cfg.add_edge ? 306 : 153, cfg.add_edge ? 180 : 115, cfg.add_edge ? 100 : 76, cfg.add_edge ? 62 : 38};
+    const int d_out[4] = {cfg.add_edge ? 180 : 115, cfg.add_edge ? 100 : 76, cfg.add_edge ? 62 : 38, 32};
+    static const char* uname[4] = {"dec.up_block4", "dec.up_block3", "dec.up_block2", "dec.up_block1"};
+    for (int i = 0; i < 4; ++i) {
+      UpBlock& u = es.up[i];
+      Block& sk = es.blk[3 - i];
+      u.in_c = d_in[i]; u.in_pad = round_up(d_in[i], 8); u.out_c = d_out[i]; u.out_pad = round_up(d_out[i], 8);
+      u.skip_c = sk.inter + sk.in_c; u.H = sk.H; u.W = sk.W;
+      u.buf = new_act(mem, mb, u.H, u.W, u.in_pad + u.out_pad);
+      u.t = new_act(mem, mb, u.H, u.W, u.out_pad);
+      u.out = new_act(mem, mb, u.H, u.W, u.out_pad);
+      const std::string P = uname[i];
+      debug_acts[P + ".out"] = {u.out, {0, u.out_c}};
+      debug_acts[P + ".up"] = {u.buf, {0, u.in_c}};
+      auto W = [&](const std::string& n) -> const HostTensor& { return sd_get(sd, P + "." + n + ".weight"); };
+      auto Bv = [&](const std::string& n) -> const HostTensor& { return sd_get(sd, P + "." + n + ".bias"); };
+      std::vector<Piece> x = {{u.buf, 0, u.in_c, 0}, {sk.buf, sk.off_out, sk.inter, 0}, {sk.buf, sk.off_x, sk.in_c, 0}};
+      build_conv(u.c11, mem, P + ".conv11", x, {{W("conv11").data.data(), Bv("conv11").data.data(), 1, 0}}, u.out_c,
+                 u.in_c + u.skip_c, 1, 1, u.H, u.W, mb);
+      set_store_epilogue(u.c11, u.t, 0, ACT_NONE);
+      finalize_conv(u.c11);
+      build_conv(u.c12, mem, P + ".conv12", {{u.t, 0, u.out_c, 0}}, {{W("conv12").data.data(), Bv("conv12").data.data(), 1, 1}},
+                 u.out_c, u.out_c, 3, 3, u.H, u.W, mb);
+      set_store_epilogue(u.c12, u.buf, u.in_pad, ACT_LRELU);
+      finalize_conv(u.c12);
+      std::vector<Piece> x21 = x;
+      x21.push_back({u.buf, u.in_pad, u.out_c, 0});
+      build_conv(u.c21, mem, P + ".conv21", x21, {{W("conv21").data.data(), Bv("conv21").data.data(), 1, 0}}, u.out_c,
+                 u.in_c + u.skip_c + u.out_c, 1, 1, u.H, u.W, mb);
+      set_store_epilogue(u.c21, u.t, 0, ACT_NONE);
+      finalize_conv(u.c21);
+      build_conv(u.c22, mem, P + ".conv22", {{u.t, 0, u.out_c, 0}}, {{W("conv22").data.data(), Bv("conv22").data.data(), 1, 1}},
+                 u.out_c, u.out_c, 3, 3, u.H, u.W, mb);
+      set_store_epilogue(u.c22, u.out, 0, ACT_LRELU);
+      finalize_conv(u.c22);
+    }
+    // final convBlock: conv1 (TC) -> fin ; conv2 + lrelu + BN -> fp32 NCHW logits (SIMT)
+    es.fin = new_act(mem, mb, 240, 320, 32);
+    debug_acts["dec.final.conv1"] = {es.fin, {0, 32}};
+    {
+      const HostTensor& w1 = sd_get(sd, "dec.final.conv1.weight");
+      const HostTensor& b1 = sd_get(sd, "dec.final.conv1.bias");
+      build_conv(es.final1, mem, "dec.final.conv1", {{es.up[3].out, 0, 32, 0}}, {{w1.data.data(), b1.data.data(), 1, 1}}, 32, 32,
+                 3, 3, 240, 320, mb);
+      set_store_epilogue(es.final1, es.fin, 0, ACT_LRELU);
+      finalize_conv(es.final1);
+      const HostTensor& w2 = sd_get(sd, "dec.final.conv2.weight");     // [3][32][3][3]
+      const HostTensor& b2 = sd_get(sd, "dec.final.conv2.bias");
+      std::vector<float> wp(9 * 32 * 3);
+      for (int co = 0; co < 3; ++co)
+        for (int c = 0; c < 32; ++c)
+          for (int t = 0; t < 9; ++t) wp[((size_t)t * 32 + c) * 3 + co] = w2.data[((size_t)co * 32 + c) * 9 + t];
+      std::vector<float> shift;
+      std::vector<float> scale = bn_scale(sd, "dec.final.bn", 3, 3, shift);
+      es.last.src = make_view(*es.fin, 0);
+      es.last.w = mem.upload(wp); es.last.bias = mem.upload(b2.data);
+      es.last.scale = mem.upload(scale); es.last.shift = mem.upload(shift);
+      es.last.H = 240; es.last.W = 320;
+    }
+    // regression head (utils.py:983-1037), fp32
+    const int Cf = 153 * (cfg.add_edge ? 2 : 1);
+    es.Cf = Cf;
+    es.hin = (float*)mem.alloc((size_t)mb * 300 * Cf * 4);
+    es.c1o = (float*)mem.alloc((size_t)mb * 14 * 18 * 128 * 4);
+    es.p1o = (float*)mem.alloc((size_t)mb * 7 * 9 * 128 * 4);
+    es.c2o = (float*)mem.alloc((size_t)mb * 5 * 7 * 128 * 4);
+    es.c3o = (float*)mem.alloc((size_t)mb * 3 * 5 * 32 * 4);
+    es.l1o = (float*)mem.alloc((size_t)mb * 256 * 4);
+    es.w_c1 = upload_hwio(mem, sd_get(sd, "elReg.c1.weight")); es.b_c1 = mem.upload(sd_get(sd, "elReg.c1.bias").data);
+    es.w_c2 = upload_hwio(mem, sd_get(sd, "elReg.c2.weight")); es.b_c2 = mem.upload(sd_get(sd, "elReg.c2.bias").data);
+    es.w_c3 = upload_hwio(mem, sd_get(sd, "elReg.c3.weight"));
+    EGN_CHECK(sd_get(sd, "elReg.c1.weight").shape[1] == Cf, "elReg.c1 input channels do not match the setting");
+    {
+      // l1 consumes the NCHW flatten c*15 + y*5 + x (utils.py:1020); our c3 output is NHWC
+      const HostTensor& w = sd_get(sd, "elReg.l1.weight");
+      std::vector<float> wp(256 * 480);
+      for (int o = 0; o < 256; ++o)
+        for (int c = 0; c < 32; ++c)
+          for (int px = 0; px < 15; ++px) wp[(size_t)o * 480 + px * 32 + c] = w.data[(size_t)o * 480 + c * 15 + px];
+      es.w_l1 = mem.upload(wp);
+      es.b_l1 = mem.upload(sd_get(sd, "elReg.l1.bias").data);
+      es.w_l2 = mem.upload(sd_get(sd, "elReg.l2.weight").data);
+      es.b_l2 = mem.upload(sd_get(sd, "elReg.l2.bias").data);
+    }
+    es.adain = nullptr;
+    if (cfg.add_seg) {
+      // StyleEncoder + MLP (RITnet_v2.py:91-121), fp32 NHWC
+      const int sh[5] = {240, 120, 60, 30, 15}, sw_[5] = {320, 160, 80, 40, 20}, sc[5] = {64, 128, 256, 256, 256};
+      es.sm = (float*)mem.alloc((size_t)mb * 76800 * 3 * 4);
+      for (int i = 0; i < 5; ++i) {
+        es.se[i] = (float*)mem.alloc((size_t)mb * sh[i] * sw_[i] * sc[i] * 4);
+        const std::string P = "seg_encoder.model." + std::to_string(i) + ".conv";
+        es.w_se[i] = upload_hwio(mem, sd_get(sd, P + ".weight"));
+        es.b_se[i] = mem.upload(sd_get(sd, P + ".bias").data);
+      }
+      es.gap = (float*)mem.alloc((size_t)mb * 256 * 4);
+      es.sty = (float*)mem.alloc((size_t)mb * cfg.style_dim * 4);
+      es.m1 = (float*)mem.alloc((size_t)mb * 256 * 4);
+      es.m2 = (float*)mem.alloc((size_t)mb * 256 * 4);
+      es.adain = (float*)mem.alloc((size_t)mb * 2 * Cf * 4);
+      es.w_se6 = mem.upload(sd_get(sd, "seg_encoder.model.6.weight").data);   // [sd][256][1][1]
+      es.b_se6 = mem.upload(sd_get(sd, "seg_encoder.model.6.bias").data);
+      for (int i = 0; i < 3; ++i) {
+        es.w_m[i] = mem.upload(sd_get(sd, "mlp.model." + std::to_string(i) + ".fc.weight").data);
+        es.b_m[i] = mem.upload(sd_get(sd, "mlp.model." + std::to_string(i) + ".fc.bias").data);
+      }
+      EGN_CHECK(sd_get(sd, "mlp.model.2.fc.weight").shape[0] == 2 * Cf, "mlp output does not match feature channels");
+    }
+    es.logits_tmp = nullptr;
+    built_esf = true;
+  }
+
+  void inorm(const Act* src, int coff, int Cv, double* sums, const Act* dst, int dcoff, int act, bool pool, int batch,
+             cudaStream_t st) {
+    CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)batch * Cv * 2 * sizeof(double), st));
+    StatsParams sp;
+    sp.src = make_view(*src, coff); sp.sums = sums; sp.B = batch; sp.HW = src->H * src->W; sp.Cv = Cv;
+    sp.slabs = std::max(1, std::min(64, sp.HW / 256));
+    dim3 grid(sp.slabs, batch);
+    instnorm_stats_kernel<<<grid, 256, (size_t)Cv * 2 * sizeof(double), st>>>(sp);
+    CUDA_OK(cudaGetLastError());
+    NormApplyParams ap;
+    ap.src = make_view(*src, coff); ap.dst = make_view(*dst, dcoff); ap.sums = sums;
+    ap.B = batch; ap.H = src->H; ap.W = src->W; ap.Cv = Cv; ap.act = act; ap.pool = pool ? 1 : 0;
+    const long long total = (long long)batch * (pool ? src->H / 2 : src->H) * (pool ? src->W / 2 : src->W) * (Cv / 8);
+    launch_1d(instnorm_apply_kernel, ap, total, st);
+    launches += 2;
+  }
+
+  void conv_f32(const float* in, const float* w, const float* bias, float* out, int B, int Hi, int Wi, int Ci, int Co,
+                int kh, int kw, int stride, int pad, int act, int reflect, cudaStream_t st) {
+    ConvF32Params p;
+    p.in = in; p.w = w; p.bias = bias; p.out = out; p.B = B; p.Hi = Hi; p.Wi = Wi; p.Ci = Ci; p.Co = Co;
+    p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad; p.act = act; p.reflect = reflect;
+    p.Ho = (Hi + 2 * pad - kh) / stride + 1; p.Wo = (Wi + 2 * pad - kw) / stride + 1;
+    launch_1d(conv_f32_kernel, p, (long long)B * p.Ho * p.Wo * Co, st);
+    ++launches;
+  }
+
+  // x, edge: device fp32 [B][H][W]; logits fp32 [B][3][H][W]; el_out [B][10]; latent [B][153]
+  void esf_forward(const float* x, const float* edge, float* logits, float* el_out, float* latent, int B, cudaStream_t st) {
+    if (!built_esf) build_esf();
+    const size_t hw = (size_t)EGN_H * EGN_W;
+    for (int b0 = 0; b0 < B; b0 += mb) {
+      const int nb = std::min(mb, B - b0);
+      const int E = nb * (cfg.add_edge ? 2 : 1);
+      const float* xi = x + b0 * hw;
+      const float* xe = edge ? edge + b0 * hw : nullptr;
+      // ---- head conv1
+      FirstConvParams fp = es.first;
+      fp.B = nb; fp.dst = make_view(*es.h1, 0, 0);
+      fp.in[0] = cfg.only_edge ? xe : xi;                     // RITnet_v2.py:276-278
+      fp.in[1] = cfg.input_concat ? xe : nullptr;             // RITnet_v2.py:279-280
+      fp.cin = cfg.input_concat ? 2 : 1;
+      fp.fstride[0] = fp.fstride[1] = fp.fstride[2] = (long long)hw;
+      EGN_CHECK(fp.in[0] != nullptr && (!cfg.input_concat || fp.in[1]), "edge input required by this setting");
+      launch_1d(first_conv_kernel, fp, (long long)nb * hw * 4, st); ++launches;
+      if (cfg.add_edge) {                                     // shared encoder on the edge map (F5)
+        EGN_CHECK(xe != nullptr, "edge input required by add_edge");
+        fp.in[0] = xe; fp.dst = make_view(*es.h1, 0, nb);
+        launch_1d(first_conv_kernel, fp, (long long)nb * hw * 4, st); ++launches;
+      }
+      run_conv(es.head2, E, st);
+      // ---- encoder blocks
+      for (int i = 0; i < 5; ++i) {
+        Block& b = es.blk[i];
+        inorm(b.buf, b.off_x, b.in_pad, b.sums_x, b.xn, 0, ACT_NONE, false, E, st);
+        run_conv(b.conv1, E, st);
+        run_conv(b.conv21, E, st);
+        run_conv(b.conv22, E, st);
+        run_conv(b.conv31, E, st);
+        run_conv(b.conv32, E, st);
+        inorm(b.buf, 0, b.inter + b.in_pad, b.sums_skip, b.tdin, 0, ACT_LRELU, i < 4, E, st);
+        run_conv(b.td, E, st);
+      }
+      // with add_edge the edge frames sit at [nb, 2nb) of every encoder buffer
+      const int eoff = nb;
+      spatial_mean_kernel<<<nb, 160, 0, st>>>(make_view(*es.bt, 0, 0), latent + (size_t)b0 * 153, nb, 300, 153);
+      CUDA_OK(cudaGetLastError()); ++launches;
+      // ---- decoder
+      for (int i = 0; i < 4; ++i) {
+        UpBlock& u = es.up[i];
+        UpsampleParams up;
+        up.B = nb; up.Hi = u.H / 2; up.Wi = u.W / 2;
+        if (i == 0) {
+          up.src = make_view(*es.bt, 0, 0); up.dst = make_view(*u.buf, 0); up.Cs = 153;
+          launch_1d(upsample2x_kernel, up, (long long)nb * u.H * u.W * up.Cs, st); ++launches;
+          if (cfg.add_edge) {                                 // x = cat(x, x_add)  RITnet_v2.py:286
+            up.src = make_view(*es.bt, 0, eoff); up.dst = make_view(*u.buf, 153);
+            launch_1d(upsample2x_kernel, up, (long long)nb * u.H * u.W * up.Cs, st); ++launches;
+          }
+        } else {
+          up.src = make_view(*es.up[i - 1].out, 0); up.dst = make_view(*u.buf, 0); up.Cs = u.in_c;
+          launch_1d(upsample2x_kernel, up, (long long)nb * u.H * u.W * up.Cs, st); ++launches;
+        }
+        run_conv(u.c11, nb, st);
+        run_conv(u.c12, nb, st);
+        run_conv(u.c21, nb, st);
+        run_conv(u.c22, nb, st);
+      }
+      run_conv(es.final1, nb, st);
+      LastConvParams lp = es.last;
+      lp.B = nb; lp.out = logits + (size_t)b0 * 3 * hw;
+      launch_1d(last_conv_kernel, lp, (long long)nb * hw, st); ++launches;
+      // ---- AdaIN parameters from the softmaxed segmentation (RITnet_v2.py:289-308)
+      if (cfg.add_seg) {
+        {
+          const long long total = (long long)nb * hw;
+          softmax3_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(lp.out, es.sm, nb, (int)hw);
+          CUDA_OK(cudaGetLastError()); ++launches;
+        }
+        conv_f32(es.sm, es.w_se[0], es.b_se[0], es.se[0], nb, 240, 320, 3, 64, 7, 7, 1, 3, ACT_RELU, 1, st);
+        const int sh[5] = {240, 120, 60, 30, 15}, sw_[5] = {320, 160, 80, 40, 20}, sc[5] = {64, 128, 256, 256, 256};
+        for (int i = 1; i < 5; ++i)
+          conv_f32(es.se[i - 1], es.w_se[i], es.b_se[i], es.se[i], nb, sh[i - 1], sw_[i - 1], sc[i - 1], sc[i], 4, 4, 2, 1,
+                   ACT_RELU, 1, st);
+        gap_f32_kernel<<<nb, 256, 0, st>>>(es.se[4], es.gap, 300, 256); CUDA_OK(cudaGetLastError());
+        linear(es.gap, es.w_se6, es.b_se6, es.sty, nb, 256, cfg.style_dim, 0, st);
+        linear(es.sty, es.w_m[0], es.b_m[0], es.m1, nb, cfg.style_dim, 256, 1, st);
+        linear(es.m1, es.w_m[1], es.b_m[1], es.m2, nb, 256, 256, 1, st);
+        linear(es.m2, es.w_m[2], es.b_m[2], es.adain, nb, 256, 2 * es.Cf, 0, st);
+        launches += 2;
+      }
+      // ---- regression head
+      HeadInputParams hp;
+      hp.src[0] = make_view(*es.bt, 0, 0); hp.src[1] = make_view(*es.bt, 0, eoff);
+      hp.nsrc = cfg.add_edge ? 2 : 1; hp.Cs = 153; hp.adain = cfg.add_seg ? es.adain : nullptr;
+      hp.out = es.hin; hp.B = nb; hp.HW = 300;
+      head_input_kernel<<<nb, 320, 0, st>>>(hp); CUDA_OK(cudaGetLastError()); ++launches;
+      conv_f32(es.hin, es.w_c1, es.b_c1, es.c1o, nb, 15, 20, es.Cf, 128, 2, 3, 1, 0, ACT_LRELU, 0, st);
+      {
+        const long long total = (long long)nb * 7 * 9 * 128;
+        avgpool_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(es.c1o, es.p1o, nb, 14, 18, 128);
+        CUDA_OK(cudaGetLastError()); ++launches;
+      }
+      conv_f32(es.p1o, es.w_c2, es.b_c2, es.c2o, nb, 7, 9, 128, 128, 3, 3, 1, 0, ACT_LRELU, 0, st);
+      conv_f32(es.c2o, es.w_c3, nullptr, es.c3o, nb, 5, 7, 128, 32, 3, 3, 1, 0, ACT_LRELU, 0, st);
+      linear(es.c3o, es.w_l1, es.b_l1, es.l1o, nb, 480, 256, 3, st);
+      linear(es.l1o, es.w_l2, es.b_l2, el_out + (size_t)b0 * 10, nb, 256, 10, 4, st);
+    }
+  }
+
+  void linear(const float* in, const float* w, const float* b, float* out, int B, int I, int O, int act, cudaStream_t st) {
+    const int total = B * O;
+    linear_kernel<<<(total + 127) / 128, 128, 0, st>>>(in, w, b, out, B, I, O, act);
+    CUDA_OK(cudaGetLastError()); ++launches;
+  }
+
+  double flops_per_frame_esf() const {
+    const int reps = cfg.add_edge ? 2 : 1;
+    double f = reps * 2.0 * 32 * (cfg.input_concat ? 2 : 1) * 9 * 240 * 320 + reps * es.head2.flops;
+    for (int i = 0; i < 5; ++i) {
+      const Block& b = es.blk[i];
+      // the reference applies TD.conv before the pool (RITnet_v2.py:42-43): count it at full size
+      const double td = 2.0 * b.op_c * (b.inter + b.in_c) * b.H * b.W;
+      f += reps * (b.conv1.flops + b.conv21.flops + b.conv22.flops + b.conv31.flops + b.conv32.flops + td);
+    }
+    for (int i = 0; i < 4; ++i) f += es.up[i].c11.flops + es.up[i].c12.flops + es.up[i].c21.flops + es.up[i].c22.flops;
+    f += es.final1.flops + 2.0 * 3 * 32 * 9 * 240 * 320;
+    f += 2.0 * (128.0 * es.Cf * 6 * 14 * 18 + 128.0 * 128 * 9 * 5 * 7 + 32.0 * 128 * 9 * 3 * 5 + 480 * 256 + 2560);
+    if (cfg.add_seg) {
+      f += 2.0 * (64.0 * 3 * 49 * 76800 + 128.0 * 64 * 16 * 19200 + 256.0 * 128 * 16 * 4800 + 256.0 * 256 * 16 * 1200 +
+                  256.0 * 256 * 16 * 300 + 256 * cfg.style_dim + cfg.style_dim * 256 + 256 * 256 + 256.0 * 2 * es.Cf);
+    }
+    return f;
+  }
+
+  double flops_per_frame_bdcn() const {
+    double f = 2.0 * 64 * 3 * 9 * 240 * 320;
+    for (int i = 1; i < 13; ++i) f += bd.vgg[i].flops;
+    for (int i = 0; i < 13; ++i) f += bd.ms_in[i].flops + bd.ms_tail[i].flops;
+    return f;
+  }
+};

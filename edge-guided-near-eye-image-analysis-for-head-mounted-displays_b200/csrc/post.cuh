@@ -1,0 +1,352 @@
+// Bandwidth-bound post-processing kernels: segmentation argmax + soft-argmax centres (K6),
+// IoU / centre-error accumulation (K7), ellipse refinement (a12).
+#pragma once
+#include "common.cuh"
+
+#define POST_SLICES 8     // row slices per frame for the soft-argmax partials
+#define POST_THREADS 256
+
+// torch.linspace(-1, 1, n)[i] in fp32 (symmetric evaluation like ATen's kernel)
+__device__ __forceinline__ float linspace_m11(int i, int n) {
+  // ATen's CPU kernel evaluates start + step*i with a fused multiply-add (checked against
+  // torch.linspace for n = 240, 320: fused matches bit for bit, unfused does not)
+  const float step = __fdiv_rn(2.0f, (float)(n - 1));
+  return i < n / 2 ? fmaf(step, (float)i, -1.0f) : fmaf(-step, (float)(n - 1 - i), 1.0f);
+}
+
+struct SoftAcc {   // online softmax expectation: weights exp(T*(v - m))
+  float m, s, sx, sy;
+};
+
+__device__ __forceinline__ void soft_add(SoftAcc& a, float v, float x, float y) {
+  if (v > a.m) {
+    const float r = __expf(4.0f * (a.m - v));
+    a.s *= r; a.sx *= r; a.sy *= r;
+    a.m = v;
+  }
+  const float e = __expf(4.0f * (v - a.m));
+  a.s += e; a.sx = fmaf(e, x, a.sx); a.sy = fmaf(e, y, a.sy);
+}
+
+__device__ __forceinline__ void soft_merge(SoftAcc& a, const SoftAcc& b) {
+  const float m = fmaxf(a.m, b.m);
+  const float ra = a.m == -INFINITY ? 0.f : __expf(4.0f * (a.m - m));
+  const float rb = b.m == -INFINITY ? 0.f : __expf(4.0f * (b.m - m));
+  a.s = a.s * ra + b.s * rb;
+  a.sx = a.sx * ra + b.sx * rb;
+  a.sy = a.sy * ra + b.sy * rb;
+  a.m = m;
+}
+
+__device__ __forceinline__ SoftAcc soft_shfl(const SoftAcc& a, int off) {
+  SoftAcc b;
+  b.m = __shfl_xor_sync(0xffffffffu, a.m, off);
+  b.s = __shfl_xor_sync(0xffffffffu, a.s, off);
+  b.sx = __shfl_xor_sync(0xffffffffu, a.sx, off);
+  b.sy = __shfl_xor_sync(0xffffffffu, a.sy, off);
+  return b;
+}
+
+// K6 pass 1: one block per (slice, frame).  Reads the fp32 NCHW logits once with 128-bit loads,
+// writes the u8 argmax (utils.py:65-81, first index wins ties) and the slice partials of the two
+// soft-argmax expectations (loss.py:16-46: pupil = channel 2, iris = -channel 0, temperature 4).
+__global__ void __launch_bounds__(POST_THREADS) seg_post_kernel(const float* __restrict__ logits,
+                                                                 uint8_t* __restrict__ argmax,
+                                                                 float* __restrict__ partial, int B) {
+  const int slice = blockIdx.x, n = blockIdx.y;
+  const int HW = EGN_H * EGN_W;
+  const int rows = EGN_H / POST_SLICES;
+  const float4* l0 = reinterpret_cast<const float4*>(logits + (size_t)n * 3 * HW);
+  const float4* l1 = l0 + HW / 4;
+  const float4* l2 = l1 + HW / 4;
+  SoftAcc pup = {-INFINITY, 0.f, 0.f, 0.f}, iri = {-INFINITY, 0.f, 0.f, 0.f};
+  const int q0 = slice * rows * (EGN_W / 4), q1 = q0 + rows * (EGN_W / 4);
+  for (int q = q0 + threadIdx.x; q < q1; q += POST_THREADS) {
+    const float4 a = __ldg(l0 + q), b = __ldg(l1 + q), c = __ldg(l2 + q);
+    const int y = q / (EGN_W / 4), x = (q % (EGN_W / 4)) * 4;
+    const float fy = linspace_m11(y, EGN_H);
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, cv[4] = {c.x, c.y, c.z, c.w};
+    uint32_t packed = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int k = 0;
+      float best = av[i];
+      if (bv[i] > best) { best = bv[i]; k = 1; }
+      if (cv[i] > best) { k = 2; }
+      packed |= (uint32_t)k << (8 * i);
+      const float fx = linspace_m11(x + i, EGN_W);
+      soft_add(pup, cv[i], fx, fy);
+      soft_add(iri, -av[i], fx, fy);
+    }
+    reinterpret_cast<uint32_t*>(argmax + (size_t)n * HW)[q] = packed;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    SoftAcc t = soft_shfl(pup, o); soft_merge(pup, t);
+    SoftAcc u = soft_shfl(iri, o); soft_merge(iri, u);
+  }
+  __shared__ SoftAcc sp[POST_THREADS / 32], si[POST_THREADS / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sp[warp] = pup; si[warp] = iri; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < POST_THREADS / 32; ++w) { soft_merge(pup, sp[w]); soft_merge(iri, si[w]); }
+    float* o = partial + ((size_t)n * POST_SLICES + slice) * 8;
+    o[0] = pup.m; o[1] = pup.s; o[2] = pup.sx; o[3] = pup.sy;
+    o[4] = iri.m; o[5] = iri.s; o[6] = iri.sx; o[7] = iri.sy;
+  }
+}
+
+// K6 pass 2: combine slices, assemble elPred = [iris_c, elOut[2:5], pupil_c, elOut[7:10]]
+// (RITnet_v2.py:334-335); without any GT mask in the batch the iris centre is elOut[5:7]
+// (RITnet_v2.py:403-408).
+__global__ void seg_post_finish_kernel(const float* __restrict__ partial, const float* __restrict__ el_out,
+                                       const float* __restrict__ cond /*[B][4] or null*/,
+                                       float* __restrict__ el_pred, int B) {
+  __shared__ int sh_any;
+  if (threadIdx.x == 0) sh_any = cond ? 0 : 1;
+  __syncthreads();
+  if (cond) {                                   // any sample with a GT mask: sum(1 - cond[:,1]) != 0
+    int any = 0;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) any |= (cond[i * 4 + 1] != 1.0f);
+    if (any) atomicOr(&sh_any, 1);
+  }
+  __syncthreads();
+  const int any_mask = sh_any;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= B) return;
+  SoftAcc pup = {-INFINITY, 0.f, 0.f, 0.f}, iri = {-INFINITY, 0.f, 0.f, 0.f};
+  for (int s = 0; s < POST_SLICES; ++s) {
+    const float* o = partial + ((size_t)n * POST_SLICES + s) * 8;
+    SoftAcc a = {o[0], o[1], o[2], o[3]}, b = {o[4], o[5], o[6], o[7]};
+    soft_merge(pup, a); soft_merge(iri, b);
+  }
+  const float* e = el_out + (size_t)n * 10;
+  float* p = el_pred + (size_t)n * 10;
+  p[0] = any_mask ? iri.sx / iri.s : e[5];
+  p[1] = any_mask ? iri.sy / iri.s : e[6];
+  p[2] = e[2]; p[3] = e[3]; p[4] = e[4];
+  p[5] = pup.sx / pup.s; p[6] = pup.sy / pup.s;
+  p[7] = e[7]; p[8] = e[8]; p[9] = e[9];
+}
+
+// ------------------------------------------------------------------------------------------
+// K7: per-frame class counts (utils.py:120-150).  label_stride: 1 (u8) or 8 (int64 little endian).
+__global__ void __launch_bounds__(256) seg_counts_kernel(const uint8_t* __restrict__ pred,
+                                                         const uint8_t* __restrict__ label, int label_stride,
+                                                         int* __restrict__ counts /*[B][9]*/, int HW) {
+  const int n = blockIdx.y;
+  int c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};     // t0 t1 t2 p0 p1 p2 i0 i1 i2
+  const uint8_t* pp = pred + (size_t)n * HW;
+  const uint8_t* ll = label + (size_t)n * HW * label_stride;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const int p = pp[i], t = ll[(size_t)i * label_stride];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      c[k] += (t == k); c[3 + k] += (p == k); c[6 + k] += (t == k && p == k);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    int v = c[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&counts[n * 9 + k], v);
+  }
+}
+
+// acc layout (double[16]):
+//  0-2  sum of per-sample IoU of class c over valid samples where the class is present in GT
+//  3-5  number of such samples
+//  6    sum pupil latent-centre error (valid: cond[:,0]==0)   10 count
+//  7    sum iris latent-centre error  (valid: cond[:,1]==0)   11 count
+//  8    sum pupil seg-centre error    (valid: cond[:,1]==0)   12 count
+//  9    sum iris seg-centre error     (valid: cond[:,1]==0)   13 count
+//  14   frames seen
+__global__ void metrics_finish_kernel(const int* __restrict__ counts, const float* __restrict__ cond /*[B][4]*/,
+                                      const float* __restrict__ pupil_c /*[B][2] px*/, const float* __restrict__ iris_c,
+                                      const float* __restrict__ el_out, const float* __restrict__ el_pred,
+                                      double* __restrict__ acc, float* __restrict__ iou_by_sample /*[B][3] or null*/, int B) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= B) return;
+  const bool seg_valid = cond[n * 4 + 1] == 0.f;
+  for (int k = 0; k < 3; ++k) {
+    const int t = counts[n * 9 + k], p = counts[n * 9 + 3 + k], i = counts[n * 9 + 6 + k];
+    float iou = NAN;
+    if (seg_valid && t > 0) {
+      iou = (float)((double)i / (double)(t + p - i));
+      atomicAdd(&acc[k], (double)i / (double)(t + p - i));
+      atomicAdd(&acc[3 + k], 1.0);
+    }
+    if (iou_by_sample) iou_by_sample[n * 3 + k] = iou;
+  }
+  // utils.py:152-162 + 636-643: pixel distance after 0.5*W*(x+1), 0.5*H*(y+1)
+  auto dist = [&](const float* gt, const float* nrm) {
+    const double dx = (double)gt[0] - 0.5 * EGN_W * ((double)nrm[0] + 1.0);
+    const double dy = (double)gt[1] - 0.5 * EGN_H * ((double)nrm[1] + 1.0);
+    return sqrt(dx * dx + dy * dy);
+  };
+  if (pupil_c && iris_c) {
+    const float* e = el_out + (size_t)n * 10;
+    const float* s = el_pred + (size_t)n * 10;
+    if (cond[n * 4 + 0] == 0.f) { atomicAdd(&acc[6], dist(pupil_c + 2 * n, e + 5)); atomicAdd(&acc[10], 1.0); }
+    if (seg_valid) {
+      atomicAdd(&acc[7], dist(iris_c + 2 * n, e + 0)); atomicAdd(&acc[11], 1.0);
+      atomicAdd(&acc[8], dist(pupil_c + 2 * n, s + 5)); atomicAdd(&acc[12], 1.0);
+      atomicAdd(&acc[9], dist(iris_c + 2 * n, s + 0)); atomicAdd(&acc[13], 1.0);
+    }
+  }
+  atomicAdd(&acc[14], 1.0);
+}
+
+// ------------------------------------------------------------------------------------------
+// a12: normalised -> pixel ellipse (helperfunctions.py:25-63,102-129 through evaluate.py:141-146)
+// and the IoU coordinate descent of utils.py:450-486, one block per ellipse, fully on device.
+struct Mat3 { double m[3][3]; };
+
+__device__ inline Mat3 mat_mul(const Mat3& a, const Mat3& b) {
+  Mat3 r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += a.m[i][k] * b.m[k][j];
+      r.m[i][j] = s;
+    }
+  return r;
+}
+__device__ inline Mat3 mat_t(const Mat3& a) {
+  Mat3 r;
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[i][j] = a.m[j][i];
+  return r;
+}
+__device__ inline Mat3 rot2d(double t) {
+  const double c = cos(t), s = sin(t);
+  Mat3 r = {{{c, -s, 0}, {s, c, 0}, {0, 0, 1}}};
+  return r;
+}
+__device__ inline Mat3 trans2d(double x, double y) {
+  Mat3 r = {{{1, 0, x}, {0, 1, y}, {0, 0, 1}}};
+  return r;
+}
+
+// conic of (cx, cy, a, b, theta)
+__device__ inline Mat3 ell_param2mat(const double* p) {
+  const Mat3 Hr = rot2d(-p[4]), Ht = trans2d(-p[0], -p[1]);
+  Mat3 Q = {{{1.0 / (p[2] * p[2]), 0, 0}, {0, 1.0 / (p[3] * p[3]), 0}, {0, 0, -1}}};
+  return mat_mul(mat_mul(mat_mul(mat_mul(mat_t(Ht), mat_t(Hr)), Q), Hr), Ht);
+}
+
+__device__ inline void ell_mat2param(const Mat3& m, double* out) {
+  const double a = m.m[0][0], b = 2 * m.m[0][1], c = m.m[1][1], d = 2 * m.m[0][2], e = 2 * m.m[1][2];
+  double th;
+  if (fabs(b) <= 1e-40 && a <= c) th = 0.0;
+  else if (fabs(b) <= 1e-40 && a > c) th = 3.14159265358979323846 / 2;
+  else th = 0.5 * atan2(b, a - c);
+  const double den = b * b - 4 * a * c;
+  const double tx = (2 * c * d - b * e) / den, ty = (2 * a * e - b * d) / den;
+  const Mat3 Hr = rot2d(th), Ht = trans2d(tx, ty);
+  const Mat3 mn = mat_mul(mat_mul(mat_mul(mat_mul(mat_t(Hr), mat_t(Ht)), m), Ht), Hr);
+  out[0] = tx; out[1] = ty; out[2] = sqrt(1.0 / mn.m[0][0]); out[3] = sqrt(1.0 / mn.m[1][1]); out[4] = th;
+}
+
+// transform with a diagonal-plus-shift homography H = [[sx,0,tx],[0,sy,ty],[0,0,1]]
+__device__ inline void ell_transform(const double* p, double sx, double sy, double tx, double ty, double* out) {
+  Mat3 Hi = {{{1.0 / sx, 0, -tx / sx}, {0, 1.0 / sy, -ty / sy}, {0, 0, 1}}};
+  const Mat3 m = mat_mul(mat_mul(mat_t(Hi), ell_param2mat(p)), Hi);
+  ell_mat2param(m, out);
+}
+
+#define REFINE_THREADS 512
+
+// IoU of the class mask against the raster of a pixel-space ellipse whose angle is in degrees
+// (utils.py:176-204 with nor=False, angle_nor=True; float32 raster arithmetic like the reference).
+__device__ float ell_iou_block(const uint8_t* __restrict__ seg, int cls, int seg_count, const double* center,
+                               const double* abt, int* sh_cnt) {
+  __shared__ float e[5];
+  if (threadIdx.x == 0) {
+    double p[5] = {center[0], center[1], abt[0], abt[1], abt[2] / 180.0 * 3.14159};
+    double o[5];
+    ell_transform(p, 2.0 / EGN_W, 2.0 / EGN_H, -1.0, -1.0, o);
+    e[0] = (float)o[0]; e[1] = (float)o[1]; e[2] = (float)o[2]; e[3] = (float)o[3];
+    e[4] = (float)o[4];
+    sh_cnt[0] = 0; sh_cnt[1] = 0;
+    // cos / sin are taken in double by the reference and then used as python floats
+    const double cc = cos(o[4]), ss = sin(o[4]);
+    reinterpret_cast<float*>(sh_cnt)[2] = (float)cc;
+    reinterpret_cast<float*>(sh_cnt)[3] = (float)ss;
+  }
+  __syncthreads();
+  const float ex = e[0], ey = e[1], ea = e[2], eb = e[3];
+  const float c = reinterpret_cast<float*>(sh_cnt)[2], s = reinterpret_cast<float*>(sh_cnt)[3];
+  int inter = 0, area = 0;
+  for (int i = threadIdx.x; i < EGN_H * EGN_W; i += REFINE_THREADS) {
+    const int y = i / EGN_W, x = i % EGN_W;
+    const float mx = linspace_m11(x, EGN_W), my = linspace_m11(y, EGN_H);
+    const float X = __fadd_rn(__fmul_rn(mx - ex, c), __fmul_rn(my - ey, s));
+    const float Y = __fadd_rn(__fmul_rn(-(mx - ex), s), __fmul_rn(my - ey, c));
+    const float qx = X / ea, qy = Y / eb;
+    const float wt = __fadd_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)), -1.0f);
+    if (wt <= 0.f) { ++area; inter += (seg[i] == cls); }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    inter += __shfl_xor_sync(0xffffffffu, inter, o);
+    area += __shfl_xor_sync(0xffffffffu, area, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&sh_cnt[0], inter); atomicAdd(&sh_cnt[1], area); }
+  __syncthreads();
+  const float I = (float)sh_cnt[0], A = (float)sh_cnt[1];
+  const float score = I / (((float)seg_count + A) - I);
+  __syncthreads();
+  return score;
+}
+
+// ell_norm: [B][2][5] normalised (iris, pupil) ellipses (elPred); out: [B][2][5] refined pixel ellipses
+// (cx, cy, a, b, theta_rad), iris first.  grid = (2, B).
+__global__ void __launch_bounds__(REFINE_THREADS) ellipse_refine_kernel(const uint8_t* __restrict__ argmax,
+                                                                         const float* __restrict__ ell_norm,
+                                                                         double* __restrict__ out, int do_refine) {
+  const int which = blockIdx.x, n = blockIdx.y;
+  const int cls = which == 0 ? 1 : 2;             // iris mask == 1, pupil mask == 2 (evaluate.py:148-151)
+  const uint8_t* seg = argmax + (size_t)n * EGN_H * EGN_W;
+  __shared__ int sh_cnt[4];
+  __shared__ int sh_seg;
+  __shared__ double px[5];
+  if (threadIdx.x == 0) {
+    sh_seg = 0;
+    double p[5];
+    for (int i = 0; i < 5; ++i) p[i] = (double)ell_norm[((size_t)n * 2 + which) * 5 + i];
+    ell_transform(p, EGN_W / 2.0, EGN_H / 2.0, EGN_W / 2.0, EGN_H / 2.0, px);
+  }
+  __syncthreads();
+  int cnt = 0;
+  for (int i = threadIdx.x; i < EGN_H * EGN_W; i += REFINE_THREADS) cnt += (seg[i] == cls);
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&sh_seg, cnt);
+  __syncthreads();
+  const int seg_count = sh_seg;
+  double center[2] = {px[0], px[1]};
+  double now[3] = {px[2], px[3], px[4] * 180.0 / 3.14159};
+  if (do_refine) {
+    float rt = ell_iou_block(seg, cls, seg_count, center, now, sh_cnt);
+    double d[3] = {1.0, 1.0, 1.0};
+    for (int tt = 0; tt < 40; ++tt) {
+      bool flag = false;
+      for (int j = 0; j < 3; ++j) {
+        now[j] -= d[j];
+        float sc = ell_iou_block(seg, cls, seg_count, center, now, sh_cnt);
+        if (sc > rt) { flag = true; continue; }
+        now[j] += 2.0 * d[j];
+        sc = ell_iou_block(seg, cls, seg_count, center, now, sh_cnt);
+        if (sc > rt) { flag = true; continue; }
+        now[j] -= d[j];
+        d[j] *= 0.8;
+      }
+      const float sc = ell_iou_block(seg, cls, seg_count, center, now, sh_cnt);
+      if (sc > rt) rt = sc;
+      if (!flag) break;
+    }
+  }
+  if (threadIdx.x == 0) {
+    double* o = out + ((size_t)n * 2 + which) * 5;
+    o[0] = center[0]; o[1] = center[1]; o[2] = now[0]; o[3] = now[1]; o[4] = now[2] / 180.0 * 3.14159;
+  }
+}

@@ -1,0 +1,118 @@
+"""Host-side mirrors of the reference's helper functions around the two modules
+(utils.calc_edge, utils.get_predictions, the metric part of test.calc_acc, evaluate.py's per-image
+path), each routed to libegn.so kernels."""
+import numpy as np
+import torch
+
+H, W = 240, 320
+
+
+def calc_edge(args, img, edge_model, device):
+    """utils.py:645-656.  The reference builds cat(img,img,img); the engine reads the grey frame
+    directly (conv1_1 weights summed over the three identical input channels)."""
+    with torch.no_grad():
+        edge = edge_model.edge(img.to(device))
+    if getattr(args, "edge_thres", 0) == 1:
+        edge = torch.where(edge >= 0.1, torch.ones_like(edge), edge)
+    return edge
+
+
+def get_predictions(output, model=None):
+    """utils.py:65-81: argmax over the class dimension as an int64 CPU tensor [B,H,W].
+
+    With ``model`` (a DenseNet2D that just produced ``output``) the device-side u8 argmax of the
+    same forward is reused, so only B*H*W bytes cross PCIe instead of the fp32 logits."""
+    if model is not None and getattr(model, "last_argmax", None) is not None \
+            and model.last_argmax.shape[0] == output.shape[0]:
+        return model.last_argmax.cpu().to(torch.int64)
+    if output.is_cuda:
+        from .engine import Context
+        ctx = _scratch_ctx(output.device)
+        el = torch.zeros((output.shape[0], 10), dtype=torch.float32, device=output.device)
+        am, _ = ctx.seg_post(output.to(torch.float32).contiguous(), el)
+        return am.cpu().to(torch.int64)
+    raise RuntimeError("egn_b200.get_predictions needs CUDA logits (no CPU fallback)")
+
+
+_scratch = {}
+
+
+def _scratch_ctx(device):
+    from .engine import Context
+    key = str(device)
+    if key not in _scratch:
+        _scratch[key] = Context(device, None, 1)
+    return _scratch[key]
+
+
+def preprocess_frames_u8(frames_u8, device):
+    """evaluate.py:102-103 / CurriculumLib.py:139-140: per-frame z-score of uint8 frames
+    [B,H,W] -> fp32 [B,1,H,W] on the device (population std, like numpy)."""
+    x = torch.as_tensor(frames_u8).to(device=device, dtype=torch.float32)
+    m = x.mean(dim=(1, 2), keepdim=True)
+    s = x.var(dim=(1, 2), keepdim=True, unbiased=False).sqrt()
+    return ((x - m) / s).unsqueeze(1).contiguous()
+
+
+class MetricAccumulator:
+    """Device-side accumulators of test.calc_acc's metrics (test.py:159-252), layout in
+    csrc/post.cuh.  ``all_reduce`` sums them across ranks (the path's only collective)."""
+    N = 16
+
+    def __init__(self, device):
+        self.acc = torch.zeros(self.N, dtype=torch.float64, device=device)
+
+    def all_reduce(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.acc, op=dist.ReduceOp.SUM)
+        return self
+
+    @staticmethod
+    def summarize(acc):
+        a = np.asarray(acc, dtype=np.float64)
+        with np.errstate(all="ignore"):
+            per = np.where(a[3:6] > 0, a[0:3] / a[3:6], np.nan)
+            d = np.where(a[10:14] > 0, a[6:10] / a[10:14], np.nan)
+        return {"mIoU": float(np.nanmean(per)) if np.isfinite(per).any() else float("nan"),
+                "IoUs": per, "pupil_latent_px": float(d[0]), "iris_latent_px": float(d[1]),
+                "pupil_seg_px": float(d[2]), "iris_seg_px": float(d[3]), "frames": int(a[14])}
+
+    def result(self):
+        return self.summarize(self.acc.cpu().numpy())
+
+
+def evaluate_batch(model, edge_model, batch, accumulator, args=None):
+    """One iteration of test.calc_acc's loop (test.py:75-214) on the engine: edge, forward,
+    argmax/centres and metric accumulation, all on the device.  ``batch`` is the reference
+    DataLoader's 9-tuple (CurriculumLib.py:139-166)."""
+    img, labels, spatW, distMap, pupil_center, iris_center, elNorm, cond, imInfo = batch
+    dev = next(model.parameters()).device
+    edge = calc_edge(args, img, edge_model, dev) if model.setting["add_edge"] or model.setting["input_concat"] \
+        or model.setting["only_edge"] or (args is not None and getattr(args, "always_edge", True)) else None
+    cond_d = cond.to(dev, torch.float32)
+    logits, el_out, latent, argmax, el_pred = model.infer(img.to(dev), edge, cond_d)
+    lab = labels.to(dev)
+    if lab.dtype not in (torch.uint8, torch.int64):
+        lab = lab.to(torch.int64)
+    model.context(dev).metrics_accumulate(argmax, lab.contiguous(), cond_d, accumulator.acc,
+                                          pupil_center.to(dev), iris_center.to(dev), el_out, el_pred)
+    return logits, el_pred, el_out, argmax
+
+
+def evaluate_ellseg_on_image(frame, model, edge_model, device=None, refine=True):
+    """evaluate.py:112-166: edge, forward, argmax, normalised->pixel ellipses and the IoU
+    refinement, returning (edge_map, seg_map, pupil_ellipse, iris_ellipse) as numpy arrays.
+    frame: [B,1,H,W] (the reference is B == 1; any B works and adds a leading axis)."""
+    assert frame.dim() == 4, "Frame must be [B,1,H,W]"
+    dev = device or next(model.parameters()).device
+    with torch.no_grad():
+        fr = frame.to(dev)
+        edge = edge_model.edge(fr)
+        logits, el_out, latent, argmax, el_pred = model.infer(fr, edge, None)
+        ell = model.context(dev).ellipse_refine(argmax, el_pred, refine)
+    ell = ell.cpu().numpy()
+    e, s = edge.squeeze(1).cpu().numpy(), argmax.cpu().numpy().astype(np.int64)
+    if frame.shape[0] == 1:
+        return e[0], s[0], ell[0, 1], ell[0, 0]
+    return e, s, ell[:, 1], ell[:, 0]

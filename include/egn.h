@@ -1,0 +1,102 @@
+/* egn.h - C ABI of libegn.so, the sm_100a engine for the edge-guided near-eye hot path.
+ *
+ * The reference has no FFI/plugin interface for this path: its boundary is the Python object
+ * protocol of two nn.Modules.  Each entry point below names the reference
+ * interface it stands behind (paths relative to the reference repository).  The Python mirrors
+ * (egn_b200.bdcn_new.BDCN, egn_b200.ritnet_v2.DenseNet2D) are the only intended callers; the
+ * ctypes binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions: every function returns 0 on success and a non-zero code on failure, after which
+ * egn_last_error() returns a thread-local message.  All tensor arguments are raw DEVICE pointers
+ * owned by the caller (fp32, contiguous, the reference's NCHW layouts) unless a parameter says
+ * "host".  `stream` is a cudaStream_t passed as void*.  A context belongs to one device and is not
+ * thread-safe.  Frames are 240x320 (utils.py:1007 hard-wires the 15x20 bottleneck).
+ */
+#ifndef EGN_H_
+#define EGN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct egn_ctx egn_ctx;
+
+/* yaml `setting` dict of models/RITnet_v2.py:204-238 (configs/<name>.yaml); unread keys omitted. */
+typedef struct egn_config {
+  int add_edge;      /* RITnet_v2.py:184,227,283 */
+  int add_seg;       /* RITnet_v2.py:231,289    */
+  int seg_detach;    /* RITnet_v2.py:291 (no effect at inference) */
+  int input_concat;  /* RITnet_v2.py:222,279    */
+  int only_edge;     /* RITnet_v2.py:276        */
+  int style_dim;     /* RITnet_v2.py:233        */
+} egn_config;
+
+enum { EGN_NET_BDCN = 0, EGN_NET_ESF = 1 };
+
+const char* egn_last_error(void);
+int egn_version(void);
+
+/* Replaces: BDCN() / DenseNet2D(setting) construction + .cuda() (test.py:280-297). */
+int egn_create(int device, const egn_config* cfg, egn_ctx** out);
+int egn_destroy(egn_ctx* ctx);
+
+/* Replaces: load_state_dict (test.py:283,295).  `blob` is a HOST buffer holding the state_dict
+ * tensors under their reference names (format: csrc/engine.cuh parse_blob). */
+int egn_set_weights(egn_ctx* ctx, int net, const void* blob, size_t bytes);
+
+/* Sizes the workspace for micro-batches of `micro_batch` frames (any caller batch is processed in
+ * such slices).  Must precede the first forward. */
+int egn_plan(egn_ctx* ctx, int micro_batch);
+
+/* Replaces: utils.calc_edge -> BDCN.forward(cat(img,img,img))[-1] (utils.py:645-651,
+ * bdcn_new.py:116-191).  x: [B,planes,240,320] with planes == 3 (what BDCN.forward receives) or
+ * planes == 1 (the grey frame calc_edge replicates; skips the cat).  edge_out: [B,1,240,320]. */
+int egn_bdcn_forward(egn_ctx* ctx, const float* x, int planes, float* edge_out, int batch, void* stream);
+
+/* Replaces: DenseNet2D.forward up to elOut (RITnet_v2.py:261-310).  x, edge: [B,1,240,320]
+ * (edge may be NULL when the setting does not read it); logits: [B,3,240,320]; el_out: [B,10];
+ * latent: [B,153]. */
+int egn_esf_forward(egn_ctx* ctx, const float* x, const float* edge, float* logits, float* el_out,
+                    float* latent, int batch, void* stream);
+
+/* Replaces: utils.get_predictions (utils.py:65-81) and the two loss.get_seg2ptLoss centres that
+ * get_allLoss folds into elPred (loss.py:16-46, RITnet_v2.py:387-412,334-335).
+ * argmax_u8: [B,240,320]; el_pred: [B,10]; cond: [B,4] fp32 or NULL - when no sample of the batch
+ * has a GT mask (sum(1-cond[:,1]) == 0) the iris centre is taken from el_out[:,5:7]. */
+int egn_seg_post(egn_ctx* ctx, const float* logits, const float* el_out, const float* cond,
+                 uint8_t* argmax_u8, float* el_pred, int batch, void* stream);
+
+/* Replaces: utils.getSeg_metrics / getPoint_metric per batch (utils.py:120-162, test.py:159-214).
+ * labels: device [B,240,320], u8 when label_is_i64 == 0 else int64; cond: [B,4] fp32;
+ * pupil_c / iris_c: [B,2] pixel centres (may both be NULL); acc: 16 doubles, accumulated into
+ * (layout in csrc/post.cuh); iou_by_sample: [B,3] fp32 or NULL. */
+int egn_metrics_accumulate(egn_ctx* ctx, const uint8_t* argmax_u8, const void* labels, int label_is_i64,
+                           const float* cond, const float* pupil_c, const float* iris_c,
+                           const float* el_out, const float* el_pred, double* acc,
+                           float* iou_by_sample, int batch, void* stream);
+
+/* Replaces: my_ellipse(norm).transform(H) + search_proper_parameter_iou_for_our_data
+ * (evaluate.py:141-151, helperfunctions.py:25-63,102-129, utils.py:176-204,450-486).
+ * ell_norm: [B,2,5] normalised ellipses (iris, pupil) = elPred; out: [B,2,5] fp64 pixel-space
+ * (cx, cy, a, b, theta); refine == 0 returns the plain transform. */
+int egn_ellipse_refine(egn_ctx* ctx, const uint8_t* argmax_u8, const float* ell_norm, double* out,
+                       int refine, int batch, void* stream);
+
+/* Introspection used by tests / bench. */
+long long egn_launch_count(egn_ctx* ctx);            /* kernels launched so far */
+double egn_flops_per_frame(egn_ctx* ctx, int net);    /* algorithmic 2*MAC of the built graph */
+/* Copies an internal activation (by debug name) to HOST fp32 [frames][C][H][W]; returns the
+ * number of floats written, or -1.  dims (host, 3 ints) receives C,H,W.  out may be NULL to query. */
+long long egn_debug_read(egn_ctx* ctx, const char* name, float* out, long long capacity, int frames,
+                         int* dims);
+/* Runs one convolution layer (by name) through both the tcgen05 kernel and its SIMT companion on
+ * the layer's current inputs and returns the max abs difference of the outputs in *max_diff. */
+int egn_conv_selfcheck(egn_ctx* ctx, const char* layer, int frames, double* max_diff, double* max_ref);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGN_H_ */
