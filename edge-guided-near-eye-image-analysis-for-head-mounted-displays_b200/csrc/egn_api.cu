@@ -171,6 +171,23 @@ int egn_ellipse_refine(egn_ctx* ctx, const uint8_t* argmax_u8, const float* ell_
   API_END
 }
 
+int egn_profile(egn_ctx* ctx, int enable) {
+  API_BEGIN
+  EGN_CHECK(ctx, "null context");
+  ctx->eng.profiling = enable != 0;
+  API_END
+}
+
+int egn_profile_read(egn_ctx* ctx, double* conv_ms, double* conv_flops, long long* conv_launches, int reset) {
+  API_BEGIN
+  EGN_CHECK(ctx && conv_ms && conv_flops && conv_launches, "bad argument");
+  CUDA_OK(cudaSetDevice(ctx->eng.device));
+  ctx->eng.profile_resolve();
+  *conv_ms = ctx->eng.prof_ms; *conv_flops = ctx->eng.prof_flops; *conv_launches = ctx->eng.prof_launches;
+  if (reset) { ctx->eng.prof_ms = 0; ctx->eng.prof_flops = 0; ctx->eng.prof_launches = 0; }
+  API_END
+}
+
 long long egn_launch_count(egn_ctx* ctx) { return ctx ? ctx->eng.launches : -1; }
 
 double egn_flops_per_frame(egn_ctx* ctx, int net) {

@@ -328,6 +328,15 @@ struct Engine {
   }
 
   void run_conv(ConvLayer& L, int batch, cudaStream_t st) {
+    if (profiling) {
+      if (prof_used >= 8192) profile_resolve();
+      profile_begin(st);
+    }
+    run_conv_impl(L, batch, st);
+    if (profiling) profile_end(st, L.flops * batch);
+  }
+
+  void run_conv_impl(ConvLayer& L, int batch, cudaStream_t st) {
     if (use_tc) {
       TcParams p = L.tc;
       p.g.batch = batch;
@@ -343,6 +352,38 @@ struct Engine {
   }
 
   long long launches = 0;
+
+  // ---- optional per-launch timing of the convolution kernel (bench.py roofline): CUDA event pairs
+  // around every conv launch on the launching stream, resolved lazily by profile_read().
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
+  double prof_flops = 0, prof_ms = 0;
+  long long prof_launches = 0;
+
+  void profile_begin(cudaStream_t st) {
+    if (prof_used == prof_events.size()) {
+      cudaEvent_t a, b;
+      CUDA_OK(cudaEventCreate(&a)); CUDA_OK(cudaEventCreate(&b));
+      prof_events.push_back({a, b});
+    }
+    CUDA_OK(cudaEventRecord(prof_events[prof_used].first, st));
+  }
+  void profile_end(cudaStream_t st, double flops) {
+    CUDA_OK(cudaEventRecord(prof_events[prof_used].second, st));
+    ++prof_used;
+    prof_flops += flops;
+    ++prof_launches;
+  }
+  void profile_resolve() {
+    for (size_t i = 0; i < prof_used; ++i) {
+      CUDA_OK(cudaEventSynchronize(prof_events[i].second));
+      float ms = 0;
+      CUDA_OK(cudaEventElapsedTime(&ms, prof_events[i].first, prof_events[i].second));
+      prof_ms += ms;
+    }
+    prof_used = 0;
+  }
 
   // ======================================================================================= BDCN
   void build_bdcn() {

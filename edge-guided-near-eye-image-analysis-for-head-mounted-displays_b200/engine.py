@@ -118,6 +118,14 @@ class Context:
     def flops_per_frame(self, net):
         return float(self.lib.egn_flops_per_frame(self.h, net))
 
+    def profile(self, enable):
+        _lib.check(self.lib.egn_profile(self.h, int(bool(enable))))
+
+    def profile_read(self, reset=True):
+        ms, fl, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+        _lib.check(self.lib.egn_profile_read(self.h, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n), int(reset)))
+        return ms.value, fl.value, n.value
+
     def debug_read(self, name, frames):
         dims = (ctypes.c_int * 3)()
         n = self.lib.egn_debug_read(self.h, name.encode(), None, 0, frames, dims)

@@ -116,3 +116,11 @@ def evaluate_ellseg_on_image(frame, model, edge_model, device=None, refine=True)
     if frame.shape[0] == 1:
         return e[0], s[0], ell[0, 1], ell[0, 0]
     return e, s, ell[:, 1], ell[:, 0]
+
+
+def shard_frames(total, rank, world):
+    """Contiguous block partition of `total` frames over `world` ranks: returns
+    (start, count); the first total % world ranks take one extra frame."""
+    base, rem = divmod(int(total), int(world))
+    start = rank * base + min(rank, rem)
+    return start, base + (1 if rank < rem else 0)

@@ -85,6 +85,12 @@ int egn_metrics_accumulate(egn_ctx* ctx, const uint8_t* argmax_u8, const void* l
 int egn_ellipse_refine(egn_ctx* ctx, const uint8_t* argmax_u8, const float* ell_norm, double* out,
                        int refine, int batch, void* stream);
 
+/* Per-launch timing of the convolution kernel (CUDA event pairs on the launching stream).
+ * egn_profile_read returns the summed kernel milliseconds, the algorithmic FLOPs (2*MAC at the
+ * reference's unpadded sizes) and the number of launches since the last reset. */
+int egn_profile(egn_ctx* ctx, int enable);
+int egn_profile_read(egn_ctx* ctx, double* conv_ms, double* conv_flops, long long* conv_launches, int reset);
+
 /* Introspection used by tests / bench. */
 long long egn_launch_count(egn_ctx* ctx);            /* kernels launched so far */
 double egn_flops_per_frame(egn_ctx* ctx, int net);    /* algorithmic 2*MAC of the built graph */

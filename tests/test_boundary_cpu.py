@@ -1,0 +1,174 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports everything
+include/egn.h declares, the look-alike modules mirror the reference's state_dict key sets, the weight
+blob format, and the multi-rank host logic (gloo, world_size 2).  No compute call touches a GPU."""
+import json
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+import egn_b200
+from egn_b200 import _lib
+from egn_b200.pack import pack_state_dict, MAGIC
+from egn_b200.shapes import bdcn_param_shapes, esf_param_shapes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CONFIGS = {
+    "baseline": dict(add_seg=0, seg_detach=0, add_edge=0, feature_channels=153, style_dim=8, input_concat=0, only_edge=0),
+    "baseline_edge": dict(add_seg=0, seg_detach=0, add_edge=1, feature_channels=153, style_dim=8, input_concat=0, only_edge=0),
+    "baseline_adain": dict(add_seg=1, seg_detach=0, add_edge=0, feature_channels=153, style_dim=8, input_concat=0, only_edge=0),
+    "baseline_adain_edge": dict(add_seg=1, seg_detach=0, add_edge=1, feature_channels=153, style_dim=8, input_concat=0, only_edge=0),
+    "baseline_input_concat": dict(add_seg=0, seg_detach=0, add_edge=0, feature_channels=153, style_dim=8, input_concat=1, only_edge=0),
+    "baseline_only_edge": dict(add_seg=0, seg_detach=0, add_edge=0, feature_channels=153, style_dim=8, input_concat=0, only_edge=1),
+}
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "egn.h")).read()
+    declared = set(re.findall(r"\b(egn_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.EXPORTS)
+    assert lib.egn_version() >= 100
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    m = egn_b200.BDCN()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 240, 320))
+    d = egn_b200.DenseNet2D(CONFIGS["baseline"])
+    with pytest.raises(RuntimeError):
+        d(torch.zeros(1, 1, 240, 320), torch.zeros(1, 1, 240, 320))
+    with pytest.raises(_lib.EgnError):
+        egn_b200.Context("cuda:0")
+
+
+def test_state_dict_keys_match_reference(golden_dir):
+    keys = json.load(open(os.path.join(golden_dir, "state_keys.json")))
+    assert {k: list(v) for k, v in bdcn_param_shapes().items()} == keys["bdcn"]
+    m = egn_b200.BDCN()
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == keys["bdcn"]
+    for name, st in CONFIGS.items():
+        d = egn_b200.DenseNet2D(st)
+        assert {k: list(v.shape) for k, v in d.state_dict().items()} == keys[name], name
+        assert {k: list(v) for k, v in esf_param_shapes(st).items()} == keys[name], name
+
+
+def test_checkpoint_containers_load_strict(tmp_path):
+    """gen_00000016.pt {'a': sd} and baseline_edge_16.pkl {'state_dict': sd, 'epoch': n}."""
+    from oracle import synth
+    p1, p2 = tmp_path / "gen_00000016.pt", tmp_path / "baseline_edge_16.pkl"
+    torch.save(synth.bdcn_checkpoint(0), p1)
+    torch.save(synth.esf_checkpoint(synth.SETTINGS["baseline_edge"], 0), p2)
+    m = egn_b200.BDCN()
+    m.load_state_dict(torch.load(p1)["a"])
+    d = egn_b200.DenseNet2D(CONFIGS["baseline_edge"])
+    d.load_state_dict(torch.load(p2)["state_dict"])
+    with pytest.raises(RuntimeError):
+        d.load_state_dict({"bogus": torch.zeros(1)})
+    with pytest.raises(AssertionError):
+        egn_b200.DenseNet2D(dict(CONFIGS["baseline_edge"], input_concat=1))     # RITnet_v2.py:273
+
+
+def test_blob_format_roundtrip():
+    sd = {"a.weight": torch.arange(6, dtype=torch.float32).reshape(2, 3), "module.b": torch.tensor(3),
+          "c": torch.zeros(0)}
+    blob = pack_state_dict(sd)
+    magic, count = struct.unpack_from("<II", blob, 0)
+    assert magic == MAGIC and count == 3
+    off = 8
+    seen = {}
+    for _ in range(count):
+        (nl,) = struct.unpack_from("<I", blob, off); off += 4
+        name = blob[off:off + nl].decode(); off += nl
+        (nd,) = struct.unpack_from("<I", blob, off); off += 4
+        dims = struct.unpack_from("<%dq" % nd, blob, off); off += 8 * nd
+        n = int(np.prod(dims)) if nd else 1
+        seen[name] = (dims, np.frombuffer(blob, "<f4", n, off).copy()); off += 4 * n
+    assert off == len(blob)
+    assert seen["a.weight"][0] == (2, 3) and seen["a.weight"][1].tolist() == [0, 1, 2, 3, 4, 5]
+    assert "b" in seen and seen["b"][1].tolist() == [3.0]           # module. prefix stripped
+
+
+def test_install_aliases():
+    import sys
+    saved = {k: sys.modules.get(k) for k in ("bdcn_new", "models", "models.RITnet_v2")}
+    try:
+        egn_b200.install()
+        from bdcn_new import BDCN
+        from models.RITnet_v2 import DenseNet2D
+        assert BDCN is egn_b200.BDCN and DenseNet2D is egn_b200.DenseNet2D
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_shard_frames_partitions_exactly():
+    for total in (0, 1, 7, 256, 4096, 4099):
+        for world in (1, 2, 3, 8):
+            spans = [egn_b200.shard_frames(total, r, world) for r in range(world)]
+            assert sum(c for _, c in spans) == total
+            pos = 0
+            for s, c in spans:
+                assert s == pos
+                pos += c
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+def test_metric_summary_matches_oracle_definition(golden_dir):
+    from oracle import graph
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    _, per, by = graph.seg_metrics(g["label"], g["pred"], g["cond"])
+    acc = np.zeros(16)
+    for i in range(by.shape[0]):
+        for c in range(3):
+            if np.isfinite(by[i, c]):
+                acc[c] += by[i, c]; acc[3 + c] += 1
+    res = egn_b200.MetricAccumulator.summarize(acc)
+    np.testing.assert_allclose(res["IoUs"], per, rtol=1e-12)
+    assert res["mIoU"] == pytest.approx(float(np.nanmean(per)))
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    acc = egn_b200.MetricAccumulator("cpu")
+    start, count = egn_b200.shard_frames(10, rank, world)
+    # each rank "evaluates" its shard: IoU of frame i for class c is (i+1)/(10*(c+1))
+    for i in range(start, start + count):
+        for c in range(3):
+            acc.acc[c] += (i + 1) / (10.0 * (c + 1)); acc.acc[3 + c] += 1
+        acc.acc[6] += float(i); acc.acc[10] += 1; acc.acc[14] += 1
+    acc.all_reduce()
+    q.put((rank, acc.result()))
+    dist.destroy_process_group()
+
+
+def test_metric_all_reduce_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for _, r in res:
+        assert r["frames"] == 10
+        np.testing.assert_allclose(r["IoUs"], [0.55, 0.275, 0.55 / 3], rtol=1e-12)
+        assert r["pupil_latent_px"] == pytest.approx(4.5)
