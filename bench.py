@@ -132,6 +132,7 @@ def main():
     ap.add_argument("--config", default="baseline_edge")
     ap.add_argument("--cpu-frames", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layer-table", default=None, help="write the per-layer kernel-time CSV of the timed region here")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -220,6 +221,10 @@ def main():
         sampler.stop_flag = True
         launches = ectx.launch_count() + mctx.launch_count() - l0
         pe, pm = ectx.profile_read(True), mctx.profile_read(True)
+        if args.layer_table and rank == 0:
+            with open(args.layer_table, "w") as f:
+                f.write(ectx.profile_table())
+                f.write(mctx.profile_table())
         ectx.profile(False); mctx.profile(False)
         for _ in range(2):
             step_e2e()

@@ -15,7 +15,7 @@ class EgnConfig(ctypes.Structure):
 EXPORTS = ["egn_last_error", "egn_version", "egn_create", "egn_destroy", "egn_set_weights", "egn_plan",
            "egn_bdcn_forward", "egn_esf_forward", "egn_seg_post", "egn_metrics_accumulate",
            "egn_ellipse_refine", "egn_launch_count", "egn_flops_per_frame", "egn_debug_read",
-           "egn_conv_selfcheck", "egn_profile", "egn_profile_read"]
+           "egn_conv_selfcheck", "egn_profile", "egn_profile_read", "egn_profile_table"]
 
 _lib = None
 
@@ -56,8 +56,11 @@ def load():
     lib.egn_profile.argtypes = [vp, ci]
     lib.egn_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                      ctypes.POINTER(cll), ci]
+    lib.egn_profile_table.argtypes = [vp, ctypes.c_char_p, cll]
+    lib.egn_profile_table.restype = cll
     for name in EXPORTS:
-        if name not in ("egn_last_error", "egn_launch_count", "egn_flops_per_frame", "egn_debug_read"):
+        if name not in ("egn_last_error", "egn_launch_count", "egn_flops_per_frame", "egn_debug_read",
+                        "egn_profile_table"):
             getattr(lib, name).restype = ci
     _lib = lib
     return lib

@@ -188,6 +188,23 @@ int egn_profile_read(egn_ctx* ctx, double* conv_ms, double* conv_flops, long lon
   API_END
 }
 
+long long egn_profile_table(egn_ctx* ctx, char* out, long long capacity) {
+  try {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->eng.device);
+    const std::string t = ctx->eng.profile_table();
+    if (out && capacity > 0) {
+      const size_t n = std::min((size_t)capacity - 1, t.size());
+      memcpy(out, t.data(), n);
+      out[n] = 0;
+    }
+    return (long long)t.size() + 1;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
 long long egn_launch_count(egn_ctx* ctx) { return ctx ? ctx->eng.launches : -1; }
 
 double egn_flops_per_frame(egn_ctx* ctx, int net) {

@@ -113,6 +113,9 @@ struct ConvLayer {
   TcParams tc{};
   SimtParams simt{};
   double flops = 0;      // algorithmic 2*MAC at unpadded sizes, per frame
+  double prof_ms = 0;    // accumulated kernel time (profiling mode)
+  double prof_frames = 0;
+  long long prof_n = 0;
 };
 
 struct EgnConfig {
@@ -333,7 +336,7 @@ struct Engine {
       profile_begin(st);
     }
     run_conv_impl(L, batch, st);
-    if (profiling) profile_end(st, L.flops * batch);
+    if (profiling) profile_end(st, L.flops * batch, &L, nullptr, batch);
   }
 
   void run_conv_impl(ConvLayer& L, int batch, cudaStream_t st) {
@@ -357,6 +360,9 @@ struct Engine {
   // around every conv launch on the launching stream, resolved lazily by profile_read().
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  struct ProfTag { ConvLayer* layer; const char* aux; int frames; };
+  std::vector<ProfTag> prof_tags;
+  std::map<std::string, std::pair<double, long long>> prof_aux;   // name -> (ms, launches)
   size_t prof_used = 0;
   double prof_flops = 0, prof_ms = 0;
   long long prof_launches = 0;
@@ -369,18 +375,36 @@ struct Engine {
     }
     CUDA_OK(cudaEventRecord(prof_events[prof_used].first, st));
   }
-  void profile_end(cudaStream_t st, double flops) {
+  void profile_end(cudaStream_t st, double flops, ConvLayer* layer, const char* aux, int frames) {
     CUDA_OK(cudaEventRecord(prof_events[prof_used].second, st));
+    if (prof_tags.size() <= prof_used) prof_tags.resize(prof_used + 1);
+    prof_tags[prof_used] = {layer, aux, frames};
     ++prof_used;
-    prof_flops += flops;
-    ++prof_launches;
+    if (layer) { prof_flops += flops; ++prof_launches; }
+  }
+  // brackets a non-conv launch sequence
+  template <typename F>
+  void aux(const char* name, cudaStream_t st, F&& fn) {
+    if (profiling) {
+      if (prof_used >= 8192) profile_resolve();
+      profile_begin(st);
+    }
+    fn();
+    if (profiling) profile_end(st, 0, nullptr, name, 0);
   }
   void profile_resolve() {
     for (size_t i = 0; i < prof_used; ++i) {
       CUDA_OK(cudaEventSynchronize(prof_events[i].second));
       float ms = 0;
       CUDA_OK(cudaEventElapsedTime(&ms, prof_events[i].first, prof_events[i].second));
-      prof_ms += ms;
+      const ProfTag& t = prof_tags[i];
+      if (t.layer) {
+        prof_ms += ms;
+        t.layer->prof_ms += ms; t.layer->prof_frames += t.frames; ++t.layer->prof_n;
+      } else {
+        auto& a = prof_aux[t.aux];
+        a.first += ms; ++a.second;
+      }
     }
     prof_used = 0;
   }
@@ -539,17 +563,18 @@ struct Engine {
       fp.B = nb; fp.cin = planes;
       fp.w = planes == 1 ? bd.first_w_gray : bd.first_w_rgb;
       for (int c = 0; c < planes; ++c) { fp.in[c] = x + ((size_t)b0 * planes + c) * hw; fp.fstride[c] = (long long)planes * hw; }
-      launch_1d(first_conv_kernel, fp, (long long)nb * hw * 8, st); ++launches;
+      aux("bdcn.first_conv", st, [&] { launch_1d(first_conv_kernel, fp, (long long)nb * hw * 8, st); ++launches; });
       static const int pool_after[13] = {-1, 0, -1, 1, -1, -1, 2, -1, -1, 3, -1, -1, -1};
       for (int i = 0; i < 13; ++i) {
         if (i > 0) run_conv(bd.vgg[i], nb, st);
         run_conv(bd.ms_in[i], nb, st);
         run_conv(bd.ms_tail[i], nb, st);
-        if (pool_after[i] >= 0) maxpool(bd.f[i], bd.pool[pool_after[i]], pool_after[i] == 3 ? 1 : 2, nb, st);
+        if (pool_after[i] >= 0)
+          aux("bdcn.maxpool", st, [&] { maxpool(bd.f[i], bd.pool[pool_after[i]], pool_after[i] == 3 ? 1 : 2, nb, st); });
       }
       BdcnTailParams tp = bd.tail;
       tp.N = nb; tp.out = edge_out + b0 * hw;
-      launch_1d(bdcn_tail_kernel, tp, (long long)nb * hw, st); ++launches;
+      aux("bdcn.tail", st, [&] { launch_1d(bdcn_tail_kernel, tp, (long long)nb * hw, st); ++launches; });
     }
   }
 
@@ -830,23 +855,23 @@ struct Engine {
       fp.cin = cfg.input_concat ? 2 : 1;
       fp.fstride[0] = fp.fstride[1] = fp.fstride[2] = (long long)hw;
       EGN_CHECK(fp.in[0] != nullptr && (!cfg.input_concat || fp.in[1]), "edge input required by this setting");
-      launch_1d(first_conv_kernel, fp, (long long)nb * hw * 4, st); ++launches;
+      aux("esf.first_conv", st, [&] { launch_1d(first_conv_kernel, fp, (long long)nb * hw * 4, st); ++launches; });
       if (cfg.add_edge) {                                     // shared encoder on the edge map (F5)
         EGN_CHECK(xe != nullptr, "edge input required by add_edge");
         fp.in[0] = xe; fp.dst = make_view(*es.h1, 0, nb);
-        launch_1d(first_conv_kernel, fp, (long long)nb * hw * 4, st); ++launches;
+        aux("esf.first_conv", st, [&] { launch_1d(first_conv_kernel, fp, (long long)nb * hw * 4, st); ++launches; });
       }
       run_conv(es.head2, E, st);
       // ---- encoder blocks
       for (int i = 0; i < 5; ++i) {
         Block& b = es.blk[i];
-        inorm(b.buf, b.off_x, b.in_pad, b.sums_x, b.xn, 0, ACT_NONE, false, E, st);
+        aux("esf.instnorm_x", st, [&] { inorm(b.buf, b.off_x, b.in_pad, b.sums_x, b.xn, 0, ACT_NONE, false, E, st); });
         run_conv(b.conv1, E, st);
         run_conv(b.conv21, E, st);
         run_conv(b.conv22, E, st);
         run_conv(b.conv31, E, st);
         run_conv(b.conv32, E, st);
-        inorm(b.buf, 0, b.inter + b.in_pad, b.sums_skip, b.tdin, 0, ACT_LRELU, i < 4, E, st);
+        aux("esf.instnorm_td", st, [&] { inorm(b.buf, 0, b.inter + b.in_pad, b.sums_skip, b.tdin, 0, ACT_LRELU, i < 4, E, st); });
         run_conv(b.td, E, st);
       }
       // with add_edge the edge frames sit at [nb, 2nb) of every encoder buffer
@@ -856,6 +881,7 @@ struct Engine {
       // ---- decoder
       for (int i = 0; i < 4; ++i) {
         UpBlock& u = es.up[i];
+        if (profiling) { if (prof_used >= 8192) profile_resolve(); profile_begin(st); }
         UpsampleParams up;
         up.B = nb; up.Hi = u.H / 2; up.Wi = u.W / 2;
         if (i == 0) {
@@ -869,6 +895,7 @@ struct Engine {
           up.src = make_view(*es.up[i - 1].out, 0); up.dst = make_view(*u.buf, 0); up.Cs = u.in_c;
           launch_1d(upsample2x_kernel, up, (long long)nb * u.H * u.W * up.Cs, st); ++launches;
         }
+        if (profiling) profile_end(st, 0, nullptr, "esf.upsample", 0);
         run_conv(u.c11, nb, st);
         run_conv(u.c12, nb, st);
         run_conv(u.c21, nb, st);
@@ -877,7 +904,7 @@ struct Engine {
       run_conv(es.final1, nb, st);
       LastConvParams lp = es.last;
       lp.B = nb; lp.out = logits + (size_t)b0 * 3 * hw;
-      launch_1d(last_conv_kernel, lp, (long long)nb * hw, st); ++launches;
+      aux("esf.last_conv", st, [&] { launch_1d(last_conv_kernel, lp, (long long)nb * hw, st); ++launches; });
       // ---- AdaIN parameters from the softmaxed segmentation (RITnet_v2.py:289-308)
       if (cfg.add_seg) {
         {
@@ -898,6 +925,7 @@ struct Engine {
         launches += 2;
       }
       // ---- regression head
+      if (profiling) { if (prof_used >= 8192) profile_resolve(); profile_begin(st); }
       HeadInputParams hp;
       hp.src[0] = make_view(*es.bt, 0, 0); hp.src[1] = make_view(*es.bt, 0, eoff);
       hp.nsrc = cfg.add_edge ? 2 : 1; hp.Cs = 153; hp.adain = cfg.add_seg ? es.adain : nullptr;
@@ -913,6 +941,7 @@ struct Engine {
       conv_f32(es.c2o, es.w_c3, nullptr, es.c3o, nb, 5, 7, 128, 32, 3, 3, 1, 0, ACT_LRELU, 0, st);
       linear(es.c3o, es.w_l1, es.b_l1, es.l1o, nb, 480, 256, 3, st);
       linear(es.l1o, es.w_l2, es.b_l2, el_out + (size_t)b0 * 10, nb, 256, 10, 4, st);
+      if (profiling) profile_end(st, 0, nullptr, "esf.reg_head", 0);
     }
   }
 
@@ -920,6 +949,25 @@ struct Engine {
     const int total = B * O;
     linear_kernel<<<(total + 127) / 128, 128, 0, st>>>(in, w, b, out, B, I, O, act);
     CUDA_OK(cudaGetLastError()); ++launches;
+  }
+
+  std::string profile_table() {
+    profile_resolve();
+    char line[512];
+    std::string out = "kind,name,H,W,kpad,cout,ntaps,n_tile,stages,launches,frames,ms_total,us_per_frame,tflops\n";
+    for (auto& kv : conv_index) {
+      ConvLayer& L = *kv.second;
+      if (L.prof_n == 0) continue;
+      snprintf(line, sizeof(line), "conv,%s,%d,%d,%d,%d,%d,%d,%d,%lld,%.0f,%.3f,%.2f,%.1f\n", L.name.c_str(), L.g.H, L.g.W,
+               L.g.kpad, L.cout, L.g.ntaps, L.tc.n_tile, L.tc.stages, L.prof_n, L.prof_frames, L.prof_ms,
+               1000.0 * L.prof_ms / L.prof_frames, L.flops * L.prof_frames / (L.prof_ms * 1e9));
+      out += line;
+    }
+    for (auto& kv : prof_aux) {
+      snprintf(line, sizeof(line), "aux,%s,,,,,,,,%lld,,%.3f,,\n", kv.first.c_str(), kv.second.second, kv.second.first);
+      out += line;
+    }
+    return out;
   }
 
   double flops_per_frame_esf() const {

@@ -126,6 +126,12 @@ class Context:
         _lib.check(self.lib.egn_profile_read(self.h, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n), int(reset)))
         return ms.value, fl.value, n.value
 
+    def profile_table(self):
+        n = self.lib.egn_profile_table(self.h, None, 0)
+        buf = ctypes.create_string_buffer(int(n))
+        self.lib.egn_profile_table(self.h, buf, n)
+        return buf.value.decode()
+
     def debug_read(self, name, frames):
         dims = (ctypes.c_int * 3)()
         n = self.lib.egn_debug_read(self.h, name.encode(), None, 0, frames, dims)

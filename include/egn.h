@@ -91,6 +91,9 @@ int egn_ellipse_refine(egn_ctx* ctx, const uint8_t* argmax_u8, const float* ell_
 int egn_profile(egn_ctx* ctx, int enable);
 int egn_profile_read(egn_ctx* ctx, double* conv_ms, double* conv_flops, long long* conv_launches, int reset);
 
+/* CSV of per-layer kernel times gathered in profiling mode; returns the bytes needed. */
+long long egn_profile_table(egn_ctx* ctx, char* out, long long capacity);
+
 /* Introspection used by tests / bench. */
 long long egn_launch_count(egn_ctx* ctx);            /* kernels launched so far */
 double egn_flops_per_frame(egn_ctx* ctx, int net);    /* algorithmic 2*MAC of the built graph */

