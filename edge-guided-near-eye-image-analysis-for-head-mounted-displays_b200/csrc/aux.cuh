@@ -31,40 +31,57 @@ struct FirstConvParams {
   int B, H, W, cout, act;
 };
 
-__global__ void first_conv_kernel(const FirstConvParams p) {
+__global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p) {
+  // weights [cin][9][cout] staged in shared memory and read as float4 (broadcast within a pixel);
+  // each thread produces 8 output channels of two horizontally adjacent pixels
+  extern __shared__ float fc_sw[];
+  const int wn = p.cin * 9 * p.cout;
+  for (int i = threadIdx.x; i < wn; i += blockDim.x) fc_sw[i] = p.w[i];
+  __syncthreads();
   const int groups = p.cout / 8;
-  const long long total = (long long)p.B * p.H * p.W * groups;
+  const int Wh = p.W / 2;
+  const long long total = (long long)p.B * p.H * Wh * groups;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int gidx = (int)(idx % groups);
-  const long long pix = idx / groups;
-  const int x = (int)(pix % p.W);
-  const int y = (int)((pix / p.W) % p.H);
-  const int n = (int)(pix / ((long long)p.W * p.H));
-  float acc[8];
+  const long long pp = idx / groups;
+  const int x = (int)(pp % Wh) * 2;
+  const int y = (int)((pp / Wh) % p.H);
+  const int n = (int)(pp / ((long long)Wh * p.H));
+  float acc0[8], acc1[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = __ldg(p.bias + gidx * 8 + i);
+  for (int i = 0; i < 8; ++i) acc0[i] = acc1[i] = __ldg(p.bias + gidx * 8 + i);
   for (int ci = 0; ci < p.cin; ++ci) {
     const float* in = p.in[ci] + (size_t)n * p.fstride[ci];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int yy = y + r - 1;
       if (yy < 0 || yy >= p.H) continue;
+      const float* row = in + (size_t)yy * p.W;
+      float a[4];
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int xx = x + s - 1;
-        if (xx < 0 || xx >= p.W) continue;
-        const float a = __ldg(in + (size_t)yy * p.W + xx);
-        const float* w = p.w + ((size_t)(ci * 9 + r * 3 + s)) * p.cout + gidx * 8;
+      for (int j = 0; j < 4; ++j) {
+        const int xx = x + j - 1;
+        a[j] = (xx >= 0 && xx < p.W) ? __ldg(row + xx) : 0.f;
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(a, __ldg(w + i), acc[i]);
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const float4* w4 = reinterpret_cast<const float4*>(fc_sw + ((size_t)(ci * 9 + r * 3 + s2)) * p.cout + gidx * 8);
+        const float4 wa = w4[0], wb = w4[1];
+        const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc0[i] = fmaf(a[s2], w[i], acc0[i]);
+          acc1[i] = fmaf(a[s2 + 1], w[i], acc1[i]);
+        }
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = apply_act(acc[i], p.act);
+  for (int i = 0; i < 8; ++i) { acc0[i] = apply_act(acc0[i], p.act); acc1[i] = apply_act(acc1[i], p.act); }
   const size_t o = ((size_t)(n + p.dst.n_off) * p.H * p.W + (size_t)y * p.W + x) * p.dst.C + p.dst.coff + gidx * 8;
-  store8(p.dst.hi, p.dst.lo, o, acc);
+  store8(p.dst.hi, p.dst.lo, o, acc0);
+  store8(p.dst.hi, p.dst.lo, o + p.dst.C, acc1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -80,9 +97,10 @@ struct LastConvParams {
   int B, H, W;
 };
 
-__global__ void last_conv_kernel(const LastConvParams p) {
-  __shared__ float sw[9 * 32 * 3];
-  for (int i = threadIdx.x; i < 9 * 32 * 3; i += blockDim.x) sw[i] = p.w[i];
+__global__ void __launch_bounds__(256) last_conv_kernel(const LastConvParams p) {
+  __shared__ float4 sw[9 * 32];           // [tap][cin] -> (w0, w1, w2, 0)
+  for (int i = threadIdx.x; i < 9 * 32; i += blockDim.x)
+    sw[i] = make_float4(p.w[i * 3], p.w[i * 3 + 1], p.w[i * 3 + 2], 0.f);
   __syncthreads();
   const long long total = (long long)p.B * p.H * p.W;
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,24 +109,26 @@ __global__ void last_conv_kernel(const LastConvParams p) {
   const int y = (int)((pix / p.W) % p.H);
   const int n = (int)(pix / ((long long)p.W * p.H));
   float a0 = p.bias[0], a1 = p.bias[1], a2 = p.bias[2];
+#pragma unroll
   for (int r = 0; r < 3; ++r) {
     const int yy = y + r - 1;
     if (yy < 0 || yy >= p.H) continue;
-    for (int s = 0; s < 3; ++s) {
-      const int xx = x + s - 1;
+#pragma unroll
+    for (int s2 = 0; s2 < 3; ++s2) {
+      const int xx = x + s2 - 1;
       if (xx < 0 || xx >= p.W) continue;
       const size_t base = ((size_t)(n + p.src.n_off) * p.H * p.W + (size_t)yy * p.W + xx) * p.src.C + p.src.coff;
-      const float* w = sw + (r * 3 + s) * 96;
+      const float4* w = sw + (r * 3 + s2) * 32;
 #pragma unroll
       for (int c8 = 0; c8 < 4; ++c8) {
         float v[8];
         load8(p.src.hi, p.src.lo, base + c8 * 8, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float* ww = w + (c8 * 8 + i) * 3;
-          a0 = fmaf(v[i], ww[0], a0);
-          a1 = fmaf(v[i], ww[1], a1);
-          a2 = fmaf(v[i], ww[2], a2);
+          const float4 ww = w[c8 * 8 + i];
+          a0 = fmaf(v[i], ww.x, a0);
+          a1 = fmaf(v[i], ww.y, a1);
+          a2 = fmaf(v[i], ww.z, a2);
         }
       }
     }
@@ -210,50 +230,64 @@ __global__ void instnorm_stats_kernel(const StatsParams p) {
 // by the caller - both are linear, so conv(pool(z)) == pool(conv(z))).
 struct NormApplyParams {
   View src, dst;
-  const double* sums;   // [B][Cv][2]
+  const double* sums;   // [B][sums_C][2]; the window's channel c sits at sums_coff + c
+  int sums_C, sums_coff;
   int B, H, W, Cv, act, pool;
 };
 
-__global__ void instnorm_apply_kernel(const NormApplyParams p) {
-  const int groups = p.Cv / 8;
-  const int Ho = p.pool ? p.H / 2 : p.H, Wo = p.pool ? p.W / 2 : p.W;
-  const long long total = (long long)p.B * Ho * Wo * groups;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int gidx = (int)(idx % groups);
-  const long long pix = idx / groups;
-  const int x = (int)(pix % Wo);
-  const int y = (int)((pix / Wo) % Ho);
-  const int n = (int)(pix / ((long long)Wo * Ho));
-  float mean[8], rstd[8];
+__global__ void __launch_bounds__(256) instnorm_apply_kernel(const NormApplyParams p) {
+  // grid (pixel slabs, frames): mean / rstd of the frame's channels are derived once per block
+  extern __shared__ float2 na_mr[];       // [Cv] (mean, rstd)
+  const int n = blockIdx.y;
   const double inv = 1.0 / ((double)p.H * p.W);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const double s = p.sums[((size_t)n * p.Cv + gidx * 8 + i) * 2];
-    const double q = p.sums[((size_t)n * p.Cv + gidx * 8 + i) * 2 + 1];
+  for (int c = threadIdx.x; c < p.Cv; c += blockDim.x) {
+    const double s = p.sums[((size_t)n * p.sums_C + p.sums_coff + c) * 2];
+    const double q = p.sums[((size_t)n * p.sums_C + p.sums_coff + c) * 2 + 1];
     const double m = s * inv;
     double var = q * inv - m * m;
     if (var < 0.0) var = 0.0;
-    mean[i] = (float)m;
-    rstd[i] = (float)(1.0 / sqrt(var + 1e-5));
+    na_mr[c] = make_float2((float)m, (float)(1.0 / sqrt(var + 1e-5)));
   }
-  float out[8];
+  __syncthreads();
+  const int groups = p.Cv / 8;
+  const int Ho = p.pool ? p.H / 2 : p.H, Wo = p.pool ? p.W / 2 : p.W;
+  const int total = Ho * Wo * groups;
+  const int per = (total + gridDim.x - 1) / gridDim.x;
+  const int i0 = blockIdx.x * per, i1 = min(total, i0 + per);
+  for (int idx = i0 + threadIdx.x; idx < i1; idx += blockDim.x) {
+    const int gidx = idx % groups;
+    const int pix = idx / groups;
+    const int x = pix % Wo, y = pix / Wo;
+    float out[8];
+    if (p.pool) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) out[i] = 0.f;
-  const int reps = p.pool ? 2 : 1;
-  for (int r = 0; r < reps; ++r)
-    for (int s = 0; s < reps; ++s) {
-      const int yy = p.pool ? y * 2 + r : y, xx = p.pool ? x * 2 + s : x;
+      for (int i = 0; i < 8; ++i) out[i] = 0.f;
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          float v[8];
+          load8(p.src.hi, p.src.lo,
+                ((size_t)(n + p.src.n_off) * p.H * p.W + (size_t)(2 * y + r) * p.W + 2 * x + s2) * p.src.C + p.src.coff + gidx * 8, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 mr = na_mr[gidx * 8 + i];
+            out[i] += apply_act((v[i] - mr.x) * mr.y, p.act);
+          }
+        }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) out[i] *= 0.25f;
+    } else {
       float v[8];
-      load8(p.src.hi, p.src.lo, ((size_t)(n + p.src.n_off) * p.H * p.W + (size_t)yy * p.W + xx) * p.src.C + p.src.coff + gidx * 8, v);
+      load8(p.src.hi, p.src.lo, ((size_t)(n + p.src.n_off) * p.H * p.W + (size_t)y * p.W + x) * p.src.C + p.src.coff + gidx * 8, v);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) out[i] += apply_act((v[i] - mean[i]) * rstd[i], p.act);
+      for (int i = 0; i < 8; ++i) {
+        const float2 mr = na_mr[gidx * 8 + i];
+        out[i] = apply_act((v[i] - mr.x) * mr.y, p.act);
+      }
     }
-  if (p.pool) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) out[i] *= 0.25f;
+    store8(p.dst.hi, p.dst.lo, ((size_t)(n + p.dst.n_off) * Ho * Wo + (size_t)y * Wo + x) * p.dst.C + p.dst.coff + gidx * 8, out);
   }
-  store8(p.dst.hi, p.dst.lo, ((size_t)(n + p.dst.n_off) * Ho * Wo + (size_t)y * Wo + x) * p.dst.C + p.dst.coff + gidx * 8, out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -264,13 +298,15 @@ struct UpsampleParams {
   int B, Hi, Wi, Cs;
 };
 
-__global__ void upsample2x_kernel(const UpsampleParams p) {
+__global__ void __launch_bounds__(256) upsample2x_kernel(const UpsampleParams p) {
+  // one thread per (output pixel, 8-channel group); Cs is a multiple of 8 (padded channels are zero)
   const int Ho = p.Hi * 2, Wo = p.Wi * 2;
-  const long long total = (long long)p.B * Ho * Wo * p.Cs;
+  const int groups = p.Cs / 8;
+  const long long total = (long long)p.B * Ho * Wo * groups;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int c = (int)(idx % p.Cs);
-  const long long pix = idx / p.Cs;
+  const int gidx = (int)(idx % groups);
+  const long long pix = idx / groups;
   const int x = (int)(pix % Wo);
   const int y = (int)((pix / Wo) % Ho);
   const int n = (int)(pix / ((long long)Wo * Ho));
@@ -280,18 +316,18 @@ __global__ void upsample2x_kernel(const UpsampleParams p) {
   const int y1 = min(y0 + 1, p.Hi - 1), x1 = min(x0 + 1, p.Wi - 1);
   const float ly = sy - y0, lx = sx - x0;
   const size_t fb = (size_t)(n + p.src.n_off) * p.Hi * p.Wi;
-  auto at = [&](int yy, int xx) {
-    const size_t i = (fb + (size_t)yy * p.Wi + xx) * p.src.C + p.src.coff + c;
-    return join_bf16(p.src.hi[i], p.src.lo[i]);
-  };
-  const float top = (1.f - lx) * at(y0, x0) + lx * at(y0, x1);
-  const float bot = (1.f - lx) * at(y1, x0) + lx * at(y1, x1);
-  const float v = (1.f - ly) * top + ly * bot;
-  bf16 h, l;
-  split_bf16(v, h, l);
-  const size_t o = ((size_t)(n + p.dst.n_off) * Ho * Wo + (size_t)y * Wo + x) * p.dst.C + p.dst.coff + c;
-  p.dst.hi[o] = h;
-  p.dst.lo[o] = l;
+  float a[8], b[8], c[8], d[8], v[8];
+  load8(p.src.hi, p.src.lo, (fb + (size_t)y0 * p.Wi + x0) * p.src.C + p.src.coff + gidx * 8, a);
+  load8(p.src.hi, p.src.lo, (fb + (size_t)y0 * p.Wi + x1) * p.src.C + p.src.coff + gidx * 8, b);
+  load8(p.src.hi, p.src.lo, (fb + (size_t)y1 * p.Wi + x0) * p.src.C + p.src.coff + gidx * 8, c);
+  load8(p.src.hi, p.src.lo, (fb + (size_t)y1 * p.Wi + x1) * p.src.C + p.src.coff + gidx * 8, d);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float top = (1.f - lx) * a[i] + lx * b[i];
+    const float bot = (1.f - lx) * c[i] + lx * d[i];
+    v[i] = (1.f - ly) * top + ly * bot;
+  }
+  store8(p.dst.hi, p.dst.lo, ((size_t)(n + p.dst.n_off) * Ho * Wo + (size_t)y * Wo + x) * p.dst.C + p.dst.coff + gidx * 8, v);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -90,9 +90,9 @@ static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
 // ---- convolution description shared by the tensor-core kernel and its SIMT reference ----
 #define EGN_MAX_TAPS 27
-#define EGN_MAX_CHUNKS 16
+#define EGN_MAX_CHUNKS 32
 #define EGN_MAX_SRC 4
-#define EGN_KC 64  // channels per K chunk (128-byte swizzled rows)
+#define EGN_KC 32  // channels per K chunk (64-byte swizzled rows)
 
 enum ConvMode { CONV_STORE = 0, CONV_MSBLOCK = 1 };
 
@@ -100,7 +100,7 @@ struct ConvGeom {
   int H, W, batch;            // output == input spatial size (stride 1, "same" padding)
   int ntaps, nchunks, groups; // groups: independent accumulators (1; 3 for the fused MSBlock tail)
   int cout_pad;               // weight rows per tap (multiple of 16)
-  int kpad;                   // nchunks * 64
+  int kpad;                   // nchunks * EGN_KC
   int8_t tap_dy[EGN_MAX_TAPS], tap_dx[EGN_MAX_TAPS], tap_grp[EGN_MAX_TAPS];
   uint8_t chunk_src[EGN_MAX_CHUNKS];
   int16_t chunk_c0[EGN_MAX_CHUNKS];
@@ -123,6 +123,9 @@ struct ConvEpi {
   bf16* out_hi;
   bf16* out_lo;
   int out_C, out_coff;
+  // optional InstanceNorm statistics of the stored values: stats[(n*stats_C + stats_coff + ch)*2 + {0: sum, 1: sum of squares}]
+  double* stats;
+  int stats_C, stats_coff;
   // CONV_MSBLOCK: v = o + sum_g relu(acc_g + b_g); score[p][j] (+)= v . score_w[j]
   const bf16* o_hi;
   const bf16* o_lo;

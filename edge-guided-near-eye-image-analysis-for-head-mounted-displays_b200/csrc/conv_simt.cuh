@@ -103,6 +103,14 @@ __global__ void __launch_bounds__(ST_THREADS) conv_simt_kernel(const SimtParams 
         v[i] = a;
       }
       store8(p.e.out_hi, p.e.out_lo, pix * p.e.out_C + p.e.out_coff + ch, v);
+      if (p.e.stats) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          double* st = p.e.stats + ((size_t)n * p.e.stats_C + p.e.stats_coff + ch + i) * 2;
+          atomicAdd(st, (double)v[i]);
+          atomicAdd(st + 1, (double)v[i] * (double)v[i]);
+        }
+      }
     }
   } else {
     float s0 = 0.f, s1 = 0.f;

@@ -2,21 +2,29 @@
 //
 //   out[n, y, x, :] = epilogue( sum_taps sum_k  A[n, y+dy, x+dx, k] * Wt[tap][:, k] )
 //
-// * GEMM view: M = 128 output pixels (an 8-row x 16-column spatial tile of one frame),
-//   N = n_tile output channels (<= 256), K = 64-channel chunks x taps.
-// * A tiles come straight from the NHWC activation planes with one 4-D TMA box
-//   {64 ch, 16 px, 8 rows, 1 frame} per (tap, chunk), shifted by the tap offset; TMA out-of-bounds
-//   zero fill implements the convolution padding for every dilation (1/2/4/8/12), and a chunk table
-//   (source buffer, channel offset, frame offset) implements channel concatenation without copies.
-// * Weight tiles {64 k, n_tile rows} come from a 2-D map over the repacked [tap][cout_pad][kpad]
-//   matrix.  Both land in shared memory in the 128-byte swizzled K-major layout UMMA consumes.
+// * GEMM view: a CTA tile is S (1 or 2) sub-tiles of M = 128 output pixels, each `sr` rows x `bw`
+//   columns of one frame (bw = 16 -> 8 rows, bw = 8 -> 16 rows), stacked in y; N = n_tile output
+//   channels (<= 256); K = 32-channel chunks x taps.
+// * A operand: per (chunk, horizontal tap offset dx) ONE 4-D TMA box {32 ch, bw px, tr + 2*dmax rows,
+//   1 frame} is loaded; every vertical tap offset dy of that dx - and both sub-tiles - read it
+//   through UMMA descriptors that start (dy + dmax) * bw (+ 128 per sub-tile) rows into the box, so
+//   a 3x3 layer fetches 3 boxes per chunk instead of 9 (the L2 -> SM path is what bounds the plain
+//   tap-per-load scheme).  TMA out-of-bounds zero fill is the convolution padding for every
+//   dilation (1/2/4/8/12); a chunk table (source buffer, channel offset, frame offset) implements
+//   channel concatenation without copies.
+// * B operand: weight tiles {32 k, n_tile rows} stream through their own ring from the repacked
+//   [tap][cout_pad][kpad] matrix; one tile feeds S sub-tiles.  Both operands use the 64-byte
+//   swizzled K-major layout.
 // * Precision: nsplit==3 issues hi*hi + lo*hi + hi*lo bf16 MMAs into one fp32 TMEM accumulator.
-// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
-//   (tcgen05.ld -> bias/activation/affine -> split-bf16 NHWC stores, or the fused MSBlock tail).
-//   smem ring (full/empty mbarriers) between producer and MMA; two TMEM accumulator buffers
-//   (tmem_full/tmem_empty) between MMA and epilogue; persistent CTAs stride over the tile list.
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue
+//   (tcgen05.ld -> bias/activation/affine -> split-bf16 NHWC stores [+ InstanceNorm sum/sumsq
+//   atomics], or the fused MSBlock tail).  Rings of full/empty mbarriers couple producer and MMA;
+//   tmem_full/tmem_empty couple MMA and epilogue (two accumulator buffers when they fit in the
+//   512 TMEM columns); persistent CTAs stride over the tile list.
 #pragma once
 #include "common.cuh"
+
+#define TC_MAX_ALOADS 8
 
 struct TcParams {
   CUtensorMap a_map[2][EGN_MAX_SRC];  // [plane hi/lo][source]
@@ -24,12 +32,19 @@ struct TcParams {
   ConvGeom g;
   ConvEpi e;
   int nsplit;                          // 1: hi*hi only, 3: split product
-  int n_tile, n_blocks, tiles_x, tiles_y, total_tiles, stages;
+  int n_tile, n_blocks, tiles_x, tiles_y, total_tiles;
+  int bw_log2, sr, S, tr, dmax, box_rows;
+  int na, nw;                          // A / W ring depths
+  uint32_t a_plane_bytes, a_box_bytes, w_plane_bytes;
+  int acc_bufs;                        // TMEM accumulator buffers (1 or 2)
+  int n_aloads;
+  int8_t aload_dx[TC_MAX_ALOADS];
+  uint8_t aload_tap0[TC_MAX_ALOADS], aload_ntaps[TC_MAX_ALOADS];
   int* err_flag;
 };
 
-#define TC_THREADS 192
-#define TC_A_BYTES 16384
+#define TC_THREADS 320
+#define TC_EPI_WARPS 8
 #define TC_ACC_STRIDE 256   // TMEM columns between the two accumulator buffers
 
 namespace tc {
@@ -93,14 +108,14 @@ __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
-// K-major, 128-byte swizzle: rows of 128 B, 8-row atoms 1024 B apart (SBO), version 1 (sm_100).
+// K-major, 64-byte swizzle: rows of 64 B (32 bf16), 8-row atoms 512 B apart (SBO), version 1.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
+  d |= (uint64_t)(512 >> 4) << 32;        // stride byte offset
   d |= (uint64_t)1 << 46;                 // descriptor version
-  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  d |= (uint64_t)4 << 61;                 // SWIZZLE_64B
   return d;
 }
 
@@ -140,39 +155,90 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// All MMAs of one (chunk, tap): NSUB sub-tiles x 2 K-steps x (1 or 3) split products, ordered so
+// that consecutive instructions target different accumulators.
+template <int NSUB, int NPL>
+__device__ __forceinline__ void issue_tap(uint32_t sA, uint32_t a_plane, uint32_t sW, uint32_t w_plane,
+                                          uint32_t d_tmem, uint32_t sub_cols, uint32_t idesc, uint32_t first) {
+  const uint64_t dA_hi = make_desc(sA), dW_hi = make_desc(sW);
+  const uint64_t dA_lo = make_desc(sA + a_plane), dW_lo = make_desc(sW + w_plane);
+#pragma unroll
+  for (int k = 0; k < EGN_KC / 16; ++k) {
+    const uint64_t koff = (uint64_t)((k * 32) >> 4);        // 16 bf16 = 32 bytes along K
+    const uint32_t acc = (k == 0) ? (first ^ 1u) : 1u;
+#pragma unroll
+    for (int s = 0; s < NSUB; ++s)
+      mma_bf16(d_tmem + s * sub_cols, dA_hi + koff + (uint64_t)(s * (8192 >> 4)), dW_hi + koff, idesc, acc);
+    if (NPL == 2) {
+#pragma unroll
+      for (int s = 0; s < NSUB; ++s)
+        mma_bf16(d_tmem + s * sub_cols, dA_lo + koff + (uint64_t)(s * (8192 >> 4)), dW_hi + koff, idesc, 1u);
+#pragma unroll
+      for (int s = 0; s < NSUB; ++s)
+        mma_bf16(d_tmem + s * sub_cols, dA_hi + koff + (uint64_t)(s * (8192 >> 4)), dW_lo + koff, idesc, 1u);
+    }
+  }
+}
+
+// Sums 32 per-lane values across the warp in 31 shuffles; lane L returns the total of v[L].
+__device__ __forceinline__ float warp_reduce32x32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
 }  // namespace tc
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;      // SWIZZLE_128B tiles need 1024-B alignment
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;      // swizzled tiles: 1024-B aligned slots
   uint8_t* smem = smem_raw + (base - raw_addr);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nplanes = p.nsplit == 1 ? 1 : 2;
-  const uint32_t w_bytes = (uint32_t)p.n_tile * 128u;
-  const uint32_t stage_bytes = nplanes * (TC_A_BYTES + w_bytes);
-  const int stages = p.stages;
+  const uint32_t a_slot_bytes = nplanes * p.a_plane_bytes;
+  const uint32_t w_slot_bytes = nplanes * p.w_plane_bytes;
+  const int na = p.na, nw = p.nw;
 
-  const uint32_t bar_base = base + stages * stage_bytes;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * stages + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * stages + 2 + b); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + stages * stage_bytes + 8 * (2 * stages + 4));
+  const uint32_t w_base = base + na * a_slot_bytes;
+  const uint32_t bar_base = w_base + nw * w_slot_bytes;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (na + s); };
+  auto w_full = [&](int s) { return bar_base + 8u * (2 * na + s); };
+  auto w_empty = [&](int s) { return bar_base + 8u * (2 * na + nw + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * na + 2 * nw + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * na + 2 * nw + 2 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (bar_base - base) + 8 * (2 * na + 2 * nw + 4));
 
   if (warp == 0 && lane == 0) {
     prefetch_map(&p.w_map[0]);
     prefetch_map(&p.a_map[0][0]);
-    for (int s = 0; s < stages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
+    for (int s = 0; s < na; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < nw; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 4);
+      mbar_init(tempty_bar(b), TC_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -185,12 +251,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int bw = 1 << p.bw_log2;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int as = 0, ws = 0;
+      uint32_t aph = 0, wph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nb = tile % p.n_blocks;
         int rest = tile / p.n_blocks;
@@ -198,158 +265,206 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         rest /= p.tiles_x;
         const int ty = rest % p.tiles_y;
         const int n = rest / p.tiles_y;
-        for (int t = 0; t < p.g.ntaps; ++t) {
-          const int x = tx * 16 + p.g.tap_dx[t];
-          const int y = ty * 8 + p.g.tap_dy[t];
-          const int wrow = t * p.g.cout_pad + nb * p.n_tile;
-          for (int c = 0; c < p.g.nchunks; ++c) {
-            mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 1);
-            mbar_expect_tx(full_bar(stage), stage_bytes);
-            const uint32_t sA = base + stage * stage_bytes;
-            const uint32_t sW = sA + nplanes * TC_A_BYTES;
-            const int src = p.g.chunk_src[c];
-            const int c0 = p.g.chunk_c0[c];
-            const int nn = n + p.g.chunk_noff[c];
-            tma_load_4d(&p.a_map[0][src], full_bar(stage), sA, c0, x, y, nn);
-            tma_load_2d(&p.w_map[0], full_bar(stage), sW, c * EGN_KC, wrow);
-            if (nplanes == 2) {
-              tma_load_4d(&p.a_map[1][src], full_bar(stage), sA + TC_A_BYTES, c0, x, y, nn);
-              tma_load_2d(&p.w_map[1], full_bar(stage), sW + w_bytes, c * EGN_KC, wrow);
+        const int x0 = tx * bw;
+        const int y0 = ty * p.tr - p.dmax;
+        for (int c = 0; c < p.g.nchunks; ++c) {
+          const int src = p.g.chunk_src[c];
+          const int c0 = p.g.chunk_c0[c];
+          const int nn = n + p.g.chunk_noff[c];
+          for (int l = 0; l < p.n_aloads; ++l) {
+            mbar_wait(a_empty(as), aph ^ 1u, p.err_flag, 1);
+            mbar_expect_tx(a_full(as), nplanes * p.a_box_bytes);
+            const uint32_t sA = base + as * a_slot_bytes;
+            tma_load_4d(&p.a_map[0][src], a_full(as), sA, c0, x0 + p.aload_dx[l], y0, nn);
+            if (nplanes == 2)
+              tma_load_4d(&p.a_map[1][src], a_full(as), sA + p.a_plane_bytes, c0, x0 + p.aload_dx[l], y0, nn);
+            if (++as == na) { as = 0; aph ^= 1u; }
+            const int t0 = p.aload_tap0[l], t1 = t0 + p.aload_ntaps[l];
+            for (int t = t0; t < t1; ++t) {
+              mbar_wait(w_empty(ws), wph ^ 1u, p.err_flag, 2);
+              mbar_expect_tx(w_full(ws), nplanes * p.w_plane_bytes);
+              const uint32_t sW = w_base + ws * w_slot_bytes;
+              const int wrow = t * p.g.cout_pad + nb * p.n_tile;
+              tma_load_2d(&p.w_map[0], w_full(ws), sW, c * EGN_KC, wrow);
+              if (nplanes == 2) tma_load_2d(&p.w_map[1], w_full(ws), sW + p.w_plane_bytes, c * EGN_KC, wrow);
+              if (++ws == nw) { ws = 0; wph ^= 1u; }
             }
-            if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
-                             ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0;
-      int ab = 0;
-      uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(ab), aphase ^ 1u, p.err_flag, 2);
-        fence_after();
-        uint32_t started = 0;
-        for (int t = 0; t < p.g.ntaps; ++t) {
-          const int grp = p.g.tap_grp[t];
-          const uint32_t d_tmem = tmem_base + ab * TC_ACC_STRIDE + grp * p.n_tile;
-          for (int c = 0; c < p.g.nchunks; ++c) {
-            mbar_wait(full_bar(stage), phase, p.err_flag, 3);
+    // The whole warp walks the schedule (convergent waits); one elected lane issues the MMAs.
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                           ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t sub_cols = (uint32_t)(p.g.groups * p.n_tile);
+    int as = 0, ws = 0;
+    uint32_t aph = 0, wph = 0;
+    int use = 0;                                   // tiles issued so far by this CTA
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++use) {
+      const int ty = (tile / (p.n_blocks * p.tiles_x)) % p.tiles_y;
+      const int nsub = min(p.S, (p.g.H - ty * p.tr + p.sr - 1) / p.sr);
+      const int ab = p.acc_bufs == 2 ? (use & 1) : 0;
+      const uint32_t aphase = (p.acc_bufs == 2 ? (use >> 1) : use) & 1u;
+      mbar_wait(tempty_bar(ab), aphase ^ 1u, p.err_flag, 3);
+      fence_after();
+      uint32_t started = 0;
+      for (int c = 0; c < p.g.nchunks; ++c) {
+        for (int l = 0; l < p.n_aloads; ++l) {
+          mbar_wait(a_full(as), aph, p.err_flag, 4);
+          const uint32_t sA = base + as * a_slot_bytes;
+          const int t0 = p.aload_tap0[l], t1 = t0 + p.aload_ntaps[l];
+          for (int t = t0; t < t1; ++t) {
+            mbar_wait(w_full(ws), wph, p.err_flag, 5);
             fence_after();
-            const uint32_t sA = base + stage * stage_bytes;
-            const uint32_t sW = sA + nplanes * TC_A_BYTES;
-            const uint64_t dA_hi = make_desc(sA);
-            const uint64_t dW_hi = make_desc(sW);
-            const uint64_t dA_lo = make_desc(sA + TC_A_BYTES);
-            const uint64_t dW_lo = make_desc(sW + w_bytes);
-#pragma unroll
-            for (int k = 0; k < EGN_KC / 16; ++k) {
-              const uint64_t koff = (uint64_t)((k * 32) >> 4);   // 16 bf16 = 32 bytes along K
-              const uint32_t acc = ((started >> grp) & 1u) | (k > 0 ? 1u : 0u);
-              mma_bf16(d_tmem, dA_hi + koff, dW_hi + koff, idesc, acc);
+            const uint32_t sW = w_base + ws * w_slot_bytes;
+            const int grp = p.g.tap_grp[t];
+            const uint32_t a_off = (uint32_t)((p.g.tap_dy[t] + p.dmax) << p.bw_log2) * 64u;
+            const uint32_t first = ((started >> grp) & 1u) ^ 1u;
+            const uint32_t d_tmem = tmem_base + ab * TC_ACC_STRIDE + grp * p.n_tile;
+            if (elect_one()) {
               if (nplanes == 2) {
-                mma_bf16(d_tmem, dA_lo + koff, dW_hi + koff, idesc, 1u);
-                mma_bf16(d_tmem, dA_hi + koff, dW_lo + koff, idesc, 1u);
+                if (nsub == 4) issue_tap<4, 2>(sA + a_off, p.a_plane_bytes, sW, p.w_plane_bytes, d_tmem, sub_cols, idesc, first);
+                else if (nsub == 2) issue_tap<2, 2>(sA + a_off, p.a_plane_bytes, sW, p.w_plane_bytes, d_tmem, sub_cols, idesc, first);
+                else if (nsub == 3) issue_tap<3, 2>(sA + a_off, p.a_plane_bytes, sW, p.w_plane_bytes, d_tmem, sub_cols, idesc, first);
+                else issue_tap<1, 2>(sA + a_off, p.a_plane_bytes, sW, p.w_plane_bytes, d_tmem, sub_cols, idesc, first);
+              } else {
+                if (nsub == 4) issue_tap<4, 1>(sA + a_off, 0, sW, 0, d_tmem, sub_cols, idesc, first);
+                else if (nsub == 2) issue_tap<2, 1>(sA + a_off, 0, sW, 0, d_tmem, sub_cols, idesc, first);
+                else if (nsub == 3) issue_tap<3, 1>(sA + a_off, 0, sW, 0, d_tmem, sub_cols, idesc, first);
+                else issue_tap<1, 1>(sA + a_off, 0, sW, 0, d_tmem, sub_cols, idesc, first);
               }
+              mma_commit(w_empty(ws));             // frees the weight slot when these MMAs retire
+              if (t + 1 == t1) mma_commit(a_empty(as));   // last tap of this box
             }
+            __syncwarp();
             started |= 1u << grp;
-            mma_commit(empty_bar(stage));          // frees the smem slot when these MMAs retire
-            if (++stage == stages) { stage = 0; phase ^= 1u; }
+            if (++ws == nw) { ws = 0; wph ^= 1u; }
           }
+          if (++as == na) { as = 0; aph ^= 1u; }
         }
-        mma_commit(tfull_bar(ab));                 // accumulator complete -> epilogue
-        ab ^= 1;
-        if (ab == 0) aphase ^= 1u;
       }
+      if (elect_one()) mma_commit(tfull_bar(ab));  // accumulators complete -> epilogue
+      __syncwarp();
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
-    const int m = quarter * 32 + lane;             // accumulator row = pixel within the tile
-    int ab = 0;
-    uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int half = (warp - 2) >> 2;              // two warps share a quarter and split the work
+    const int m = quarter * 32 + lane;             // accumulator row = pixel within the sub-tile
+    const int mr = m >> p.bw_log2, mc = m & (bw - 1);
+    float* stat_buf = reinterpret_cast<float*>(smem + (bar_base - base) + 8 * (2 * na + 2 * nw + 4) + 16);
+    int stat_flip = 0;
+    int use = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++use) {
       const int nb = tile % p.n_blocks;
       int rest = tile / p.n_blocks;
       const int tx = rest % p.tiles_x;
       rest /= p.tiles_x;
       const int ty = rest % p.tiles_y;
       const int n = rest / p.tiles_y;
-      const int py = ty * 8 + (m >> 4);
-      const int px = tx * 16 + (m & 15);
-      const bool valid = (py < p.g.H) && (px < p.g.W);
-      const size_t pix = ((size_t)n * p.g.H + py) * p.g.W + px;
+      const int nsub = min(p.S, (p.g.H - ty * p.tr + p.sr - 1) / p.sr);
+      const int ab = p.acc_bufs == 2 ? (use & 1) : 0;
+      const uint32_t aphase = (p.acc_bufs == 2 ? (use >> 1) : use) & 1u;
+      const int px = tx * bw + mc;
 
-      mbar_wait(tfull_bar(ab), aphase, p.err_flag, 4);
+      mbar_wait(tfull_bar(ab), aphase, p.err_flag, 6);
       fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * TC_ACC_STRIDE;
 
       if (p.e.mode == CONV_STORE) {
-        for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(tbase + c0, r);
-          tmem_ld_wait();
+        const int per_sub = p.n_tile >> 4;         // 16-column groups per sub-tile
+        for (int g = half; g < per_sub; g += 2) {   // a warp keeps its channel groups across sub-tiles
+          const int c0 = g << 4;
           const int cb = nb * p.n_tile + c0;      // first output channel of this 16-column group
-          if (valid) {
+          float sacc[32];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int ch = cb + h * 8;
-              if (ch + 8 <= p.e.cout_store) {
-                float v[8];
+          for (int i = 0; i < 32; ++i) sacc[i] = 0.f;
+          for (int s = 0; s < nsub; ++s) {
+            const int py = ty * p.tr + s * p.sr + mr;
+            const bool valid = (py < p.g.H) && (px < p.g.W);
+            const size_t pix = ((size_t)n * p.g.H + py) * p.g.W + px;
+            uint32_t r[16];
+            tmem_ld16(tbase + s * p.n_tile + c0, r);
+            tmem_ld_wait();
+            float v[16];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  float a = __uint_as_float(r[h * 8 + i]) + __ldg(p.e.bias + ch + i);
-                  a = apply_act(a, p.e.act);
-                  if (p.e.post_scale) a = a * __ldg(p.e.post_scale + ch + i) + __ldg(p.e.post_shift + ch + i);
-                  v[i] = a;
-                }
-                store8(p.e.out_hi, p.e.out_lo, pix * p.e.out_C + p.e.out_coff + ch, v);
+            for (int i = 0; i < 16; ++i) {
+              float a = 0.f;
+              if (valid && cb + i < p.e.cout_store) {
+                a = __uint_as_float(r[i]) + __ldg(p.e.bias + cb + i);
+                a = apply_act(a, p.e.act);
+                if (p.e.post_scale) a = a * __ldg(p.e.post_scale + cb + i) + __ldg(p.e.post_shift + cb + i);
               }
+              v[i] = a;
             }
+            if (valid) {
+              if (cb + 8 <= p.e.cout_store) store8(p.e.out_hi, p.e.out_lo, pix * p.e.out_C + p.e.out_coff + cb, v);
+              if (cb + 16 <= p.e.cout_store) store8(p.e.out_hi, p.e.out_lo, pix * p.e.out_C + p.e.out_coff + cb + 8, v + 8);
+            }
+            if (p.e.stats) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { sacc[i] += v[i]; sacc[16 + i] = fmaf(v[i], v[i], sacc[16 + i]); }
+            }
+          }
+          if (p.e.stats) {
+            // InstanceNorm statistics of what was stored: warp butterfly, then the four lane-quarter
+            // warps of this half combine through shared memory -> 32 atomics per (tile, group)
+            const float tot = warp_reduce32x32(sacc, lane);
+            float* sb = stat_buf + ((half * 2 + (stat_flip & 1)) * 4) * 32;
+            sb[quarter * 32 + lane] = tot;
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+            if (quarter == 0) {
+              const float t4 = sb[lane] + sb[32 + lane] + sb[64 + lane] + sb[96 + lane];
+              const int ch = cb + (lane & 15);
+              if (ch < p.e.cout_store)
+                atomicAdd(p.e.stats + ((size_t)n * p.e.stats_C + p.e.stats_coff + ch) * 2 + (lane >> 4), (double)t4);
+            }
+            ++stat_flip;
           }
         }
       } else {
         // fused MSBlock tail (bdcn_new.py:49-55 + conv*_down/score_dsn* collapsed)
-        float s0 = 0.f, s1 = 0.f;
-        for (int c0 = 0; c0 < 32; c0 += 16) {
-          uint32_t r0[16], r1[16], r2[16];
-          tmem_ld16(tbase + c0, r0);
-          tmem_ld16(tbase + 32 + c0, r1);
-          tmem_ld16(tbase + 64 + c0, r2);
-          tmem_ld_wait();
-          if (valid) {
-            float o[16];
-            load8(p.e.o_hi, p.e.o_lo, pix * 32 + c0, o);
-            load8(p.e.o_hi, p.e.o_lo, pix * 32 + c0 + 8, o + 8);
+        for (int s = half; s < nsub; s += 2) {
+          const int py = ty * p.tr + s * p.sr + mr;
+          const bool valid = (py < p.g.H) && (px < p.g.W);
+          const size_t pix = ((size_t)n * p.g.H + py) * p.g.W + px;
+          float s0 = 0.f, s1 = 0.f;
+          for (int c0 = 0; c0 < 32; c0 += 16) {
+            uint32_t r0[16], r1[16], r2[16];
+            tmem_ld16(tbase + (s * 3 + 0) * 32 + c0, r0);
+            tmem_ld16(tbase + (s * 3 + 1) * 32 + c0, r1);
+            tmem_ld16(tbase + (s * 3 + 2) * 32 + c0, r2);
+            tmem_ld_wait();
+            if (valid) {
+              float o[16];
+              load8(p.e.o_hi, p.e.o_lo, pix * 32 + c0, o);
+              load8(p.e.o_hi, p.e.o_lo, pix * 32 + c0 + 8, o + 8);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int ch = c0 + i;
-              float v = o[i];
-              v += fmaxf(__uint_as_float(r0[i]) + __ldg(p.e.bias + ch), 0.f);
-              v += fmaxf(__uint_as_float(r1[i]) + __ldg(p.e.bias + p.g.cout_pad + ch), 0.f);
-              v += fmaxf(__uint_as_float(r2[i]) + __ldg(p.e.bias + 2 * p.g.cout_pad + ch), 0.f);
-              s0 += v * __ldg(p.e.score_w + ch);
-              s1 += v * __ldg(p.e.score_w + 32 + ch);
+              for (int i = 0; i < 16; ++i) {
+                const int ch = c0 + i;
+                float v = o[i];
+                v += fmaxf(__uint_as_float(r0[i]) + __ldg(p.e.bias + ch), 0.f);
+                v += fmaxf(__uint_as_float(r1[i]) + __ldg(p.e.bias + p.g.cout_pad + ch), 0.f);
+                v += fmaxf(__uint_as_float(r2[i]) + __ldg(p.e.bias + 2 * p.g.cout_pad + ch), 0.f);
+                s0 += v * __ldg(p.e.score_w + ch);
+                s1 += v * __ldg(p.e.score_w + 32 + ch);
+              }
             }
           }
-        }
-        if (valid) {
-          float2* dst = reinterpret_cast<float2*>(p.e.score) + pix;
-          float2 cur = p.e.score_accum ? *dst : make_float2(0.f, 0.f);
-          cur.x += s0;
-          cur.y += s1;
-          *dst = cur;
+          if (valid) {
+            float2* dst = reinterpret_cast<float2*>(p.e.score) + pix;
+            float2 cur = p.e.score_accum ? *dst : make_float2(0.f, 0.f);
+            cur.x += s0;
+            cur.y += s1;
+            *dst = cur;
+          }
         }
       }
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(ab));
-      ab ^= 1;
-      if (ab == 0) aphase ^= 1u;
     }
   }
 
@@ -384,54 +499,90 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// 4-D map over an NHWC bf16 plane: dims (C, W, H, N), box (64, 16, 8, 1), 128-B swizzle.
-static void make_act_map(CUtensorMap* map, const bf16* ptr, int N, int H, int W, int C) {
+// 4-D map over an NHWC bf16 plane: dims (C, W, H, N), box (32, bw, box_rows, 1), 64-B swizzle.
+static void make_act_map(CUtensorMap* map, const bf16* ptr, int N, int H, int W, int C, int bw, int box_rows) {
   EGN_CHECK(C % 8 == 0, "activation channels must be a multiple of 8");
+  EGN_CHECK(box_rows >= 1 && box_rows <= 256, "activation box rows out of range");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {EGN_KC, 16, 8, 1};
+  cuuint32_t box[4] = {EGN_KC, (cuuint32_t)bw, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides,
-                               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   EGN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
 }
 
-// 2-D map over the packed weights [rows = ntaps*cout_pad][kpad], box (64, n_tile).
+// 2-D map over the packed weights [rows = ntaps*cout_pad][kpad], box (32, n_tile).
 static void make_w_map(CUtensorMap* map, const bf16* ptr, int rows, int kpad, int n_tile) {
   cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)kpad * 2};
   cuuint32_t box[2] = {EGN_KC, (cuuint32_t)n_tile};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, dims, strides,
-                               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   EGN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
 }
 
 static size_t tc_smem_bytes(const TcParams& p) {
   const int nplanes = p.nsplit == 1 ? 1 : 2;
-  const size_t stage = (size_t)nplanes * (TC_A_BYTES + (size_t)p.n_tile * 128);
-  return 1024 + p.stages * stage + 8 * (2 * p.stages + 4) + 16;
+  return 1024 + (size_t)p.na * nplanes * p.a_plane_bytes + (size_t)p.nw * nplanes * p.w_plane_bytes +
+         8 * (2 * p.na + 2 * p.nw + 4) + 16 + 2 * 2 * 4 * 32 * sizeof(float);
 }
 
-// Fills the tiling fields of `p` from geometry + cout and picks the pipeline depth.
+// Fills the tiling fields of `p` from the geometry (taps must be sorted by dx) and sizes the rings.
 static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
+  const ConvGeom& g = p.g;
   p.nsplit = nsplit;
   p.n_blocks = ceil_div(cout_pad, 256);
   EGN_CHECK(cout_pad % (16 * p.n_blocks) == 0, "cout_pad must split into equal 16-aligned N tiles");
   p.n_tile = cout_pad / p.n_blocks;
   EGN_CHECK(p.n_tile % 16 == 0 && p.n_tile <= 256, "bad n_tile");
-  EGN_CHECK(p.g.groups * p.n_tile <= TC_ACC_STRIDE, "accumulator groups exceed a TMEM buffer");
-  p.tiles_x = ceil_div(p.g.W, 16);
-  p.tiles_y = ceil_div(p.g.H, 8);
-  p.total_tiles = p.tiles_x * p.tiles_y * p.g.batch * p.n_blocks;
+  // sub-tile shape: 8 rows x 16 px or 16 rows x 8 px, whichever covers the frame with less padding
+  auto padded = [&](int bw) { const int sr = 128 / bw; return (long long)round_up(g.W, bw) * round_up(g.H, sr); };
+  const int bw = padded(8) < padded(16) ? 8 : 16;
+  p.bw_log2 = bw == 8 ? 3 : 4;
+  p.sr = 128 / bw;
+  const int cols = g.groups * p.n_tile;
+  EGN_CHECK(cols <= 512, "accumulator groups exceed TMEM");
+  // more sub-tiles per CTA tile amortise the weight stream and give the MMA pipe independent
+  // accumulators to interleave; prefer shapes that keep two TMEM buffers
+  p.S = 1;
+  const int rows_avail = ceil_div(g.H, p.sr);
+  if (rows_avail >= 2 && 2 * cols <= 512) p.S = 2;
+  if (rows_avail >= 4 && 4 * cols <= TC_ACC_STRIDE) p.S = 4;
+  p.tr = p.S * p.sr;
+  p.acc_bufs = p.S * cols <= TC_ACC_STRIDE ? 2 : 1;
+  p.tiles_x = ceil_div(g.W, bw);
+  p.tiles_y = ceil_div(g.H, p.tr);
+  p.total_tiles = p.tiles_x * p.tiles_y * g.batch * p.n_blocks;
+  // A boxes: one per distinct dx, covering every dy
+  p.dmax = 0;
+  p.n_aloads = 0;
+  for (int t = 0; t < g.ntaps; ++t) {
+    p.dmax = std::max(p.dmax, std::abs((int)g.tap_dy[t]));
+    if (p.n_aloads == 0 || p.aload_dx[p.n_aloads - 1] != g.tap_dx[t]) {
+      for (int l = 0; l < p.n_aloads; ++l) EGN_CHECK(p.aload_dx[l] != g.tap_dx[t], "taps must be grouped by dx");
+      EGN_CHECK(p.n_aloads < TC_MAX_ALOADS, "too many distinct horizontal tap offsets");
+      p.aload_dx[p.n_aloads] = g.tap_dx[t];
+      p.aload_tap0[p.n_aloads] = (uint8_t)t;
+      p.aload_ntaps[p.n_aloads] = 0;
+      ++p.n_aloads;
+    }
+    ++p.aload_ntaps[p.n_aloads - 1];
+  }
+  p.box_rows = p.tr + 2 * p.dmax;
+  p.a_box_bytes = (uint32_t)p.box_rows * bw * 64u;
+  p.a_plane_bytes = (p.a_box_bytes + 1023u) & ~1023u;
+  p.w_plane_bytes = (uint32_t)p.n_tile * 64u;
   const int nplanes = nsplit == 1 ? 1 : 2;
-  const size_t stage = (size_t)nplanes * (TC_A_BYTES + (size_t)p.n_tile * 128);
-  int st = (int)((200 * 1024) / stage);
-  if (st > 8) st = 8;
-  EGN_CHECK(st >= 2, "pipeline needs at least two stages");
-  p.stages = st;
+  const size_t budget = 227 * 1024 - 1024 - 512 - 2048;
+  const size_t a_slot = (size_t)nplanes * p.a_plane_bytes, w_slot = (size_t)nplanes * p.w_plane_bytes;
+  p.na = 2;
+  EGN_CHECK(budget > p.na * a_slot + 2 * w_slot, "conv_tc: tile does not fit in shared memory");
+  p.nw = (int)std::min<size_t>(8, (budget - p.na * a_slot) / w_slot);
+  while (p.na < 4 && budget >= (p.na + 1) * a_slot + (size_t)p.nw * w_slot) ++p.na;
 }
 
 static void tc_launch(const TcParams& p, int num_sms, cudaStream_t stream) {

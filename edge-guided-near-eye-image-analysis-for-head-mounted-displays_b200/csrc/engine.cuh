@@ -154,8 +154,8 @@ struct Engine {
   struct Block {
     Act *buf, *xn, *t, *tdin;
     int in_c, in_pad, inter, op_c, off_out, off_x, off_x1, off_x22, H, W;
-    double* sums_x;
-    double* sums_skip;
+    double* stats;      // [E][inter + in_pad][2]: sum / sum of squares per buffer channel of [out | x]
+    int stats_C;
     ConvLayer conv1, conv21, conv22, conv31, conv32, td;
   };
   struct UpBlock {
@@ -178,6 +178,8 @@ struct Engine {
     float *sm, *se[5], *gap, *sty, *m1, *m2, *adain;
     float *w_se[5], *b_se[5], *w_se6, *b_se6, *w_m[3], *b_m[3];
     float* logits_tmp;
+    double* stats_all;
+    size_t stats_bytes;
   } es;
 
   ~Engine() {
@@ -254,20 +256,25 @@ struct Engine {
     }
     g.nchunks = nch;
     g.kpad = nch * EGN_KC;
-    // ---- taps
-    int t = 0;
+    // ---- taps, grouped by horizontal offset: the tensor-core kernel loads one activation box per
+    // distinct dx and serves every dy of it from that box
+    struct TapRef { int gi, r, s, dy, dx; };
+    std::vector<TapRef> taps;
     for (int gi = 0; gi < g.groups; ++gi)
       for (int r = 0; r < kh; ++r)
-        for (int s = 0; s < kw; ++s, ++t) {
-          g.tap_dy[t] = (int8_t)(r * specs[gi].dil - specs[gi].pad);
-          g.tap_dx[t] = (int8_t)(s * specs[gi].dil - specs[gi].pad);
-          g.tap_grp[t] = (int8_t)gi;
-        }
+        for (int s = 0; s < kw; ++s)
+          taps.push_back({gi, r, s, r * specs[gi].dil - specs[gi].pad, s * specs[gi].dil - specs[gi].pad});
+    std::stable_sort(taps.begin(), taps.end(), [](const TapRef& a, const TapRef& b) { return a.dx < b.dx; });
+    for (int t = 0; t < g.ntaps; ++t) {
+      g.tap_dy[t] = (int8_t)taps[t].dy;
+      g.tap_dx[t] = (int8_t)taps[t].dx;
+      g.tap_grp[t] = (int8_t)taps[t].gi;
+    }
     // ---- weights
     const size_t wn = (size_t)g.ntaps * g.cout_pad * g.kpad;
     std::vector<bf16> whi(wn, host_bf16(0.f)), wlo(wn, host_bf16(0.f));
     std::vector<float> bias((size_t)g.groups * g.cout_pad, 0.f);
-    for (int gi = 0; gi < g.groups; ++gi) {
+    {
       int ref_c = 0;
       for (size_t i = 0; i < pieces.size(); ++i) {
         const Piece& pc = pieces[i];
@@ -275,20 +282,22 @@ struct Engine {
         for (int j = 0; j < pc.len; ++j, ++ref_c) {
           const int rel = pc.buf_c - v.c_lo + j;
           const int kidx = (v.first_chunk + rel / EGN_KC) * EGN_KC + rel % EGN_KC;
-          for (int co = 0; co < cout; ++co)
-            for (int r = 0; r < kh; ++r)
-              for (int s = 0; s < kw; ++s) {
-                const float wv = specs[gi].w[(((size_t)co * cin + ref_c) * kh + r) * kw + s];
-                const size_t o = ((size_t)(gi * kh * kw + r * kw + s) * g.cout_pad + co) * g.kpad + kidx;
-                const bf16 h = host_bf16(wv);
-                whi[o] = h;
-                wlo[o] = host_bf16(wv - __bfloat162float(h));
-              }
+          for (int t = 0; t < g.ntaps; ++t) {
+            const TapRef& tr = taps[t];
+            for (int co = 0; co < cout; ++co) {
+              const float wv = specs[tr.gi].w[(((size_t)co * cin + ref_c) * kh + tr.r) * kw + tr.s];
+              const size_t o = ((size_t)t * g.cout_pad + co) * g.kpad + kidx;
+              const bf16 h = host_bf16(wv);
+              whi[o] = h;
+              wlo[o] = host_bf16(wv - __bfloat162float(h));
+            }
+          }
         }
       }
+    }
+    for (int gi = 0; gi < g.groups; ++gi)
       if (specs[gi].bias)
         for (int co = 0; co < cout; ++co) bias[(size_t)gi * g.cout_pad + co] = specs[gi].bias[co];
-    }
     L.w_hi = mem.upload(whi);
     L.w_lo = mem.upload(wlo);
     L.e.bias = mem.upload(bias);
@@ -306,6 +315,10 @@ struct Engine {
     EGN_CHECK(coff % 8 == 0 && coff + L.e.cout_store <= dst->C, L.name + ": destination channel window");
   }
 
+  void set_stats(ConvLayer& L, double* stats, int stats_C, int stats_coff) {
+    L.e.stats = stats; L.e.stats_C = stats_C; L.e.stats_coff = stats_coff;
+  }
+
   void finalize_conv(ConvLayer& L) {
     conv_index[L.name] = &L;
     // SIMT companion
@@ -318,8 +331,8 @@ struct Engine {
       tc_configure(L.tc, L.g.cout_pad, nsplit);
       for (int s = 0; s < L.nsrc; ++s) {
         const Act* a = L.src_act[s];
-        make_act_map(&L.tc.a_map[0][s], a->hi, a->N, a->H, a->W, a->C);
-        make_act_map(&L.tc.a_map[1][s], a->lo, a->N, a->H, a->W, a->C);
+        make_act_map(&L.tc.a_map[0][s], a->hi, a->N, a->H, a->W, a->C, 1 << L.tc.bw_log2, L.tc.box_rows);
+        make_act_map(&L.tc.a_map[1][s], a->lo, a->N, a->H, a->W, a->C, 1 << L.tc.bw_log2, L.tc.box_rows);
       }
       for (int s = L.nsrc; s < EGN_MAX_SRC; ++s) {
         L.tc.a_map[0][s] = L.tc.a_map[0][0];
@@ -563,7 +576,7 @@ struct Engine {
       fp.B = nb; fp.cin = planes;
       fp.w = planes == 1 ? bd.first_w_gray : bd.first_w_rgb;
       for (int c = 0; c < planes; ++c) { fp.in[c] = x + ((size_t)b0 * planes + c) * hw; fp.fstride[c] = (long long)planes * hw; }
-      aux("bdcn.first_conv", st, [&] { launch_1d(first_conv_kernel, fp, (long long)nb * hw * 8, st); ++launches; });
+      aux("bdcn.first_conv", st, [&] { launch_first(fp, st); });
       static const int pool_after[13] = {-1, 0, -1, 1, -1, -1, 2, -1, -1, 3, -1, -1, -1};
       for (int i = 0; i < 13; ++i) {
         if (i > 0) run_conv(bd.vgg[i], nb, st);
@@ -630,13 +643,21 @@ struct Engine {
       b.t = new_act(mem, E, b.H, b.W, inter[i]);
       const bool pool = i < 4;
       b.tdin = new_act(mem, E, pool ? b.H / 2 : b.H, pool ? b.W / 2 : b.W, inter[i] + b.in_pad);
-      b.sums_x = (double*)mem.alloc((size_t)E * b.in_pad * 2 * sizeof(double));
-      b.sums_skip = (double*)mem.alloc((size_t)E * (inter[i] + b.in_pad) * 2 * sizeof(double));
+      b.stats_C = inter[i] + b.in_pad;
       const std::string P = bname[i];
       debug_acts[P + ".x"] = {b.buf, {b.off_x, b.in_c}};
       debug_acts[P + ".x1"] = {b.buf, {b.off_x1, b.inter}};
       debug_acts[P + ".x22"] = {b.buf, {b.off_x22, b.inter}};
       debug_acts[P + ".out"] = {b.buf, {b.off_out, b.inter}};
+    }
+    // InstanceNorm statistics come from the producing convolutions' epilogues (one array, one memset)
+    {
+      size_t tot = 0;
+      for (int i = 0; i < 5; ++i) tot += (size_t)E * es.blk[i].stats_C * 2;
+      es.stats_all = (double*)mem.alloc(tot * sizeof(double));
+      es.stats_bytes = tot * sizeof(double);
+      size_t off = 0;
+      for (int i = 0; i < 5; ++i) { es.blk[i].stats = es.stats_all + off; off += (size_t)E * es.blk[i].stats_C * 2; }
     }
     // head: conv1 (SIMT first layer) -> h1; conv2 + lrelu + BN -> block1.x   (utils.py:1046-1050)
     {
@@ -658,6 +679,7 @@ struct Engine {
       std::vector<float> shift;
       std::vector<float> scale = bn_scale(sd, "enc.head.bn", 32, es.head2.g.cout_pad, shift);
       set_store_epilogue(es.head2, es.blk[0].buf, es.blk[0].off_x, ACT_LRELU, mem.upload(scale), mem.upload(shift));
+      set_stats(es.head2, es.blk[0].stats, es.blk[0].stats_C, es.blk[0].off_x);
       finalize_conv(es.head2);
     }
     for (int i = 0; i < 5; ++i) {
@@ -688,6 +710,7 @@ struct Engine {
       build_conv(b.conv32, mem, P + ".conv32", {{b.t, 0, b.inter, 0}}, {{W("conv32").data.data(), Bv("conv32").data.data(), 1, 1}},
                  b.inter, b.inter, 3, 3, b.H, b.W, E);
       set_store_epilogue(b.conv32, b.buf, b.off_out, ACT_LRELU);
+      set_stats(b.conv32, b.stats, b.stats_C, b.off_out);
       finalize_conv(b.conv32);
       // TD: IN -> lrelu -> (pool) -> 1x1 conv on skip = [out, x]   RITnet_v2.py:40-44,65-66
       const Act* dst = i < 4 ? es.blk[i + 1].buf : es.bt;
@@ -696,6 +719,7 @@ struct Engine {
                  {{W("TD.conv").data.data(), Bv("TD.conv").data.data(), 1, 0}}, b.op_c, b.inter + b.in_c, 1, 1,
                  b.tdin->H, b.tdin->W, E);
       set_store_epilogue(b.td, dst, dst_off, ACT_NONE);
+      if (i < 4) set_stats(b.td, es.blk[i + 1].stats, es.blk[i + 1].stats_C, es.blk[i + 1].off_x);
       finalize_conv(b.td);
     }
     // decoder
@@ -705,7 +729,11 @@ struct Engine {
     for (int i = 0; i < 4; ++i) {
       UpBlock& u = es.up[i];
       Block& sk = es.blk[3 - i];
-      u.in_c = d_in[i]; u.in_pad = round_up(d_in[i], 8); u.out_c = d_out[i]; u.out_pad = round_up(d_out[i], 8);
+      u.in_c = d_in[i]; u.out_c = d_out[i]; u.out_pad = round_up(d_out[i], 8);
+      // the upsampled input occupies [0, in_pad); with add_edge the first block's input is
+      // cat(x, x_edge) (RITnet_v2.py:286) and each 153-channel half gets its own 8-aligned slot
+      const bool two_halves = (i == 0 && cfg.add_edge);
+      u.in_pad = two_halves ? 2 * 160 : round_up(d_in[i], 8);
       u.skip_c = sk.inter + sk.in_c; u.H = sk.H; u.W = sk.W;
       u.buf = new_act(mem, mb, u.H, u.W, u.in_pad + u.out_pad);
       u.t = new_act(mem, mb, u.H, u.W, u.out_pad);
@@ -715,7 +743,11 @@ struct Engine {
       debug_acts[P + ".up"] = {u.buf, {0, u.in_c}};
       auto W = [&](const std::string& n) -> const HostTensor& { return sd_get(sd, P + "." + n + ".weight"); };
       auto Bv = [&](const std::string& n) -> const HostTensor& { return sd_get(sd, P + "." + n + ".bias"); };
-      std::vector<Piece> x = {{u.buf, 0, u.in_c, 0}, {sk.buf, sk.off_out, sk.inter, 0}, {sk.buf, sk.off_x, sk.in_c, 0}};
+      std::vector<Piece> x;
+      if (two_halves) { x.push_back({u.buf, 0, 153, 0}); x.push_back({u.buf, 160, 153, 0}); }
+      else x.push_back({u.buf, 0, u.in_c, 0});
+      x.push_back({sk.buf, sk.off_out, sk.inter, 0});
+      x.push_back({sk.buf, sk.off_x, sk.in_c, 0});
       build_conv(u.c11, mem, P + ".conv11", x, {{W("conv11").data.data(), Bv("conv11").data.data(), 1, 0}}, u.out_c,
                  u.in_c + u.skip_c, 1, 1, u.H, u.W, mb);
       set_store_epilogue(u.c11, u.t, 0, ACT_NONE);
@@ -811,21 +843,25 @@ struct Engine {
     built_esf = true;
   }
 
-  void inorm(const Act* src, int coff, int Cv, double* sums, const Act* dst, int dcoff, int act, bool pool, int batch,
-             cudaStream_t st) {
-    CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)batch * Cv * 2 * sizeof(double), st));
-    StatsParams sp;
-    sp.src = make_view(*src, coff); sp.sums = sums; sp.B = batch; sp.HW = src->H * src->W; sp.Cv = Cv;
-    sp.slabs = std::max(1, std::min(64, sp.HW / 256));
-    dim3 grid(sp.slabs, batch);
-    instnorm_stats_kernel<<<grid, 256, (size_t)Cv * 2 * sizeof(double), st>>>(sp);
+  void launch_first(const FirstConvParams& fp, cudaStream_t st) {
+    const long long total = (long long)fp.B * fp.H * (fp.W / 2) * (fp.cout / 8);
+    const size_t smem = (size_t)fp.cin * 9 * fp.cout * sizeof(float);
+    first_conv_kernel<<<(unsigned)((total + 255) / 256), 256, smem, st>>>(fp);
     CUDA_OK(cudaGetLastError());
+    ++launches;
+  }
+
+  // y = act((x - mean) * rstd) [-> 2x2 average pool]; the statistics were accumulated by the producers' epilogues
+  void inorm(const Act* src, int coff, int Cv, const double* stats, int stats_C, const Act* dst, int dcoff, int act,
+             bool pool, int batch, cudaStream_t st) {
     NormApplyParams ap;
-    ap.src = make_view(*src, coff); ap.dst = make_view(*dst, dcoff); ap.sums = sums;
+    ap.src = make_view(*src, coff); ap.dst = make_view(*dst, dcoff); ap.sums = stats; ap.sums_C = stats_C; ap.sums_coff = coff;
     ap.B = batch; ap.H = src->H; ap.W = src->W; ap.Cv = Cv; ap.act = act; ap.pool = pool ? 1 : 0;
-    const long long total = (long long)batch * (pool ? src->H / 2 : src->H) * (pool ? src->W / 2 : src->W) * (Cv / 8);
-    launch_1d(instnorm_apply_kernel, ap, total, st);
-    launches += 2;
+    const long long per_frame = (long long)(pool ? src->H / 2 : src->H) * (pool ? src->W / 2 : src->W) * (Cv / 8);
+    dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(64, per_frame / 2048)), (unsigned)batch);
+    instnorm_apply_kernel<<<grid, 256, (size_t)Cv * sizeof(float2), st>>>(ap);
+    CUDA_OK(cudaGetLastError());
+    launches += 1;
   }
 
   void conv_f32(const float* in, const float* w, const float* bias, float* out, int B, int Hi, int Wi, int Ci, int Co,
@@ -855,23 +891,24 @@ struct Engine {
       fp.cin = cfg.input_concat ? 2 : 1;
       fp.fstride[0] = fp.fstride[1] = fp.fstride[2] = (long long)hw;
       EGN_CHECK(fp.in[0] != nullptr && (!cfg.input_concat || fp.in[1]), "edge input required by this setting");
-      aux("esf.first_conv", st, [&] { launch_1d(first_conv_kernel, fp, (long long)nb * hw * 4, st); ++launches; });
+      aux("esf.first_conv", st, [&] { launch_first(fp, st); });
       if (cfg.add_edge) {                                     // shared encoder on the edge map (F5)
         EGN_CHECK(xe != nullptr, "edge input required by add_edge");
         fp.in[0] = xe; fp.dst = make_view(*es.h1, 0, nb);
-        aux("esf.first_conv", st, [&] { launch_1d(first_conv_kernel, fp, (long long)nb * hw * 4, st); ++launches; });
+        aux("esf.first_conv", st, [&] { launch_first(fp, st); });
       }
+      CUDA_OK(cudaMemsetAsync(es.stats_all, 0, es.stats_bytes, st));
       run_conv(es.head2, E, st);
       // ---- encoder blocks
       for (int i = 0; i < 5; ++i) {
         Block& b = es.blk[i];
-        aux("esf.instnorm_x", st, [&] { inorm(b.buf, b.off_x, b.in_pad, b.sums_x, b.xn, 0, ACT_NONE, false, E, st); });
+        aux("esf.instnorm_x", st, [&] { inorm(b.buf, b.off_x, b.in_pad, b.stats, b.stats_C, b.xn, 0, ACT_NONE, false, E, st); });
         run_conv(b.conv1, E, st);
         run_conv(b.conv21, E, st);
         run_conv(b.conv22, E, st);
         run_conv(b.conv31, E, st);
         run_conv(b.conv32, E, st);
-        aux("esf.instnorm_td", st, [&] { inorm(b.buf, 0, b.inter + b.in_pad, b.sums_skip, b.tdin, 0, ACT_LRELU, i < 4, E, st); });
+        aux("esf.instnorm_td", st, [&] { inorm(b.buf, 0, b.inter + b.in_pad, b.stats, b.stats_C, b.tdin, 0, ACT_LRELU, i < 4, E, st); });
         run_conv(b.td, E, st);
       }
       // with add_edge the edge frames sit at [nb, 2nb) of every encoder buffer
@@ -885,15 +922,15 @@ struct Engine {
         UpsampleParams up;
         up.B = nb; up.Hi = u.H / 2; up.Wi = u.W / 2;
         if (i == 0) {
-          up.src = make_view(*es.bt, 0, 0); up.dst = make_view(*u.buf, 0); up.Cs = 153;
-          launch_1d(upsample2x_kernel, up, (long long)nb * u.H * u.W * up.Cs, st); ++launches;
+          up.src = make_view(*es.bt, 0, 0); up.dst = make_view(*u.buf, 0); up.Cs = 160;
+          launch_1d(upsample2x_kernel, up, (long long)nb * u.H * u.W * (up.Cs / 8), st); ++launches;
           if (cfg.add_edge) {                                 // x = cat(x, x_add)  RITnet_v2.py:286
-            up.src = make_view(*es.bt, 0, eoff); up.dst = make_view(*u.buf, 153);
-            launch_1d(upsample2x_kernel, up, (long long)nb * u.H * u.W * up.Cs, st); ++launches;
+            up.src = make_view(*es.bt, 0, eoff); up.dst = make_view(*u.buf, 160);
+            launch_1d(upsample2x_kernel, up, (long long)nb * u.H * u.W * (up.Cs / 8), st); ++launches;
           }
         } else {
-          up.src = make_view(*es.up[i - 1].out, 0); up.dst = make_view(*u.buf, 0); up.Cs = u.in_c;
-          launch_1d(upsample2x_kernel, up, (long long)nb * u.H * u.W * up.Cs, st); ++launches;
+          up.src = make_view(*es.up[i - 1].out, 0); up.dst = make_view(*u.buf, 0); up.Cs = es.up[i - 1].out_pad;
+          launch_1d(upsample2x_kernel, up, (long long)nb * u.H * u.W * (up.Cs / 8), st); ++launches;
         }
         if (profiling) profile_end(st, 0, nullptr, "esf.upsample", 0);
         run_conv(u.c11, nb, st);
@@ -954,12 +991,12 @@ struct Engine {
   std::string profile_table() {
     profile_resolve();
     char line[512];
-    std::string out = "kind,name,H,W,kpad,cout,ntaps,n_tile,stages,launches,frames,ms_total,us_per_frame,tflops\n";
+    std::string out = "kind,name,H,W,kpad,cout,ntaps,n_tile,S_na_nw,launches,frames,ms_total,us_per_frame,tflops\n";
     for (auto& kv : conv_index) {
       ConvLayer& L = *kv.second;
       if (L.prof_n == 0) continue;
       snprintf(line, sizeof(line), "conv,%s,%d,%d,%d,%d,%d,%d,%d,%lld,%.0f,%.3f,%.2f,%.1f\n", L.name.c_str(), L.g.H, L.g.W,
-               L.g.kpad, L.cout, L.g.ntaps, L.tc.n_tile, L.tc.stages, L.prof_n, L.prof_frames, L.prof_ms,
+               L.g.kpad, L.cout, L.g.ntaps, L.tc.n_tile, L.tc.S * 100 + L.tc.na * 10 + L.tc.nw, L.prof_n, L.prof_frames, L.prof_ms,
                1000.0 * L.prof_ms / L.prof_frames, L.flops * L.prof_frames / (L.prof_ms * 1e9));
       out += line;
     }
