@@ -38,6 +38,8 @@ struct TcParams {
   uint32_t a_plane_bytes, a_box_bytes, w_plane_bytes;
   int acc_bufs;                        // TMEM accumulator buffers (1 or 2)
   int n_aloads;
+  int l2_prefetch;                     // producer prefetches its next tile's activation boxes into L2
+  int dbg;                             // timing experiments only: 1 = skip epilogue body, 2 = skip MMAs, 4 = skip TMA loads
   int8_t aload_dx[TC_MAX_ALOADS];
   uint8_t aload_tap0[TC_MAX_ALOADS], aload_ntaps[TC_MAX_ALOADS];
   int* err_flag;
@@ -102,6 +104,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar
       " [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+
+// Pulls a box into L2 only (no shared-memory destination, no barrier).
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
@@ -190,6 +198,40 @@ __device__ __forceinline__ void issue_tap(uint32_t sA, uint32_t a_plane, uint32_
   }
 }
 
+// Two fp32 -> packed bf16x2 hi and lo words (hi = rn(x), lo = rn(x - hi)).
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float ra = a - __uint_as_float(hi << 16);
+  const float rb = b - __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// 16 consecutive channels of one pixel to both planes as one 32-byte store each (full sectors).
+__device__ __forceinline__ void store16(bf16* hi, bf16* lo, size_t idx, const float v[16]) {
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split_pack2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(hi + idx), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(lo + idx), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7]) : "memory");
+}
+
+__device__ __forceinline__ void load16(const bf16* hi, const bf16* lo, size_t idx, float v[16]) {
+  uint32_t h[8], l[8];
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]), "=r"(h[4]), "=r"(h[5]), "=r"(h[6]), "=r"(h[7]) : "l"(hi + idx));
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(l[0]), "=r"(l[1]), "=r"(l[2]), "=r"(l[3]), "=r"(l[4]), "=r"(l[5]), "=r"(l[6]), "=r"(l[7]) : "l"(lo + idx));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[2 * i] = __uint_as_float(h[i] << 16) + __uint_as_float(l[i] << 16);
+    v[2 * i + 1] = __uint_as_float(h[i] & 0xffff0000u) + __uint_as_float(l[i] & 0xffff0000u);
+  }
+}
+
 // Sums 32 per-lane values across the warp in 31 shuffles; lane L returns the total of v[L].
 __device__ __forceinline__ float warp_reduce32x32(float (&v)[32], int lane) {
 #pragma unroll
@@ -247,6 +289,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                  ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // epilogue constants (bias per accumulator group, optional post-activation affine, MSBlock score
+  // weights) are read from shared memory by the epilogue warps
+  float* stat_buf = reinterpret_cast<float*>(smem + (bar_base - base) + 8 * (2 * na + 2 * nw + 4) + 16);
+  float* c_bias = stat_buf + 2 * 2 * 4 * 32;       // [groups * cout_pad] <= 768
+  float* c_scale = c_bias + 768;                   // [cout_pad] <= 512   (MSBlock: score_w[64])
+  float* c_shift = c_scale + 512;                  // [cout_pad] <= 512
+  for (int i = threadIdx.x; i < p.g.groups * p.g.cout_pad; i += blockDim.x) c_bias[i] = p.e.bias[i];
+  if (p.e.post_scale)
+    for (int i = threadIdx.x; i < p.g.cout_pad; i += blockDim.x) { c_scale[i] = p.e.post_scale[i]; c_shift[i] = p.e.post_shift[i]; }
+  if (p.e.mode == CONV_MSBLOCK)
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) c_scale[i] = p.e.score_w[i];
   fence_before();
   __syncthreads();
   fence_after();
@@ -267,6 +320,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int n = rest / p.tiles_y;
         const int x0 = tx * bw;
         const int y0 = ty * p.tr - p.dmax;
+        // the activations stream from HBM: pull this CTA's next tile into L2 while this one computes,
+        // so the ring's loads see L2 latency instead of DRAM latency (one box per chunk covers all dx
+        // but the outermost pixel columns)
+        if (p.l2_prefetch && nb == 0) {
+          const int nt = tile + gridDim.x * p.n_blocks;   // same nb, next spatial tile of this CTA
+          if (nt < p.total_tiles) {
+            int r2 = nt / p.n_blocks;
+            const int ptx = r2 % p.tiles_x;
+            r2 /= p.tiles_x;
+            const int pty = r2 % p.tiles_y;
+            const int pn = r2 / p.tiles_y;
+            for (int c = 0; c < p.g.nchunks; ++c) {
+              const int src = p.g.chunk_src[c];
+              tma_prefetch_4d(&p.a_map[0][src], p.g.chunk_c0[c], ptx * bw, pty * p.tr - p.dmax, pn + p.g.chunk_noff[c]);
+              if (nplanes == 2)
+                tma_prefetch_4d(&p.a_map[1][src], p.g.chunk_c0[c], ptx * bw, pty * p.tr - p.dmax, pn + p.g.chunk_noff[c]);
+            }
+          }
+        }
         for (int c = 0; c < p.g.nchunks; ++c) {
           const int src = p.g.chunk_src[c];
           const int c0 = p.g.chunk_c0[c];
@@ -324,7 +396,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const uint32_t first = ((started >> grp) & 1u) ^ 1u;
             const uint32_t d_tmem = tmem_base + ab * TC_ACC_STRIDE + grp * p.n_tile;
             if (elect_one()) {
-              if (nplanes == 2) {
+              if (p.dbg & 2) {
+              } else if (nplanes == 2) {
                 if (nsub == 4) issue_tap<4, 2>(sA + a_off, p.a_plane_bytes, sW, p.w_plane_bytes, d_tmem, sub_cols, idesc, first);
                 else if (nsub == 2) issue_tap<2, 2>(sA + a_off, p.a_plane_bytes, sW, p.w_plane_bytes, d_tmem, sub_cols, idesc, first);
                 else if (nsub == 3) issue_tap<3, 2>(sA + a_off, p.a_plane_bytes, sW, p.w_plane_bytes, d_tmem, sub_cols, idesc, first);
@@ -354,7 +427,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int half = (warp - 2) >> 2;              // two warps share a quarter and split the work
     const int m = quarter * 32 + lane;             // accumulator row = pixel within the sub-tile
     const int mr = m >> p.bw_log2, mc = m & (bw - 1);
-    float* stat_buf = reinterpret_cast<float*>(smem + (bar_base - base) + 8 * (2 * na + 2 * nw + 4) + 16);
     int stat_flip = 0;
     int use = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++use) {
@@ -373,39 +445,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * TC_ACC_STRIDE;
 
-      if (p.e.mode == CONV_STORE) {
+      if (p.dbg & 1) {
+      } else if (p.e.mode == CONV_STORE) {
         const int per_sub = p.n_tile >> 4;         // 16-column groups per sub-tile
+        const bool has_post = p.e.post_scale != nullptr;
         for (int g = half; g < per_sub; g += 2) {   // a warp keeps its channel groups across sub-tiles
           const int c0 = g << 4;
           const int cb = nb * p.n_tile + c0;      // first output channel of this 16-column group
+          float bias[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = reinterpret_cast<const float4*>(c_bias + cb)[i];
+            bias[4 * i] = b4.x; bias[4 * i + 1] = b4.y; bias[4 * i + 2] = b4.z; bias[4 * i + 3] = b4.w;
+          }
           float sacc[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) sacc[i] = 0.f;
-          for (int s = 0; s < nsub; ++s) {
-            const int py = ty * p.tr + s * p.sr + mr;
-            const bool valid = (py < p.g.H) && (px < p.g.W);
-            const size_t pix = ((size_t)n * p.g.H + py) * p.g.W + px;
-            uint32_t r[16];
-            tmem_ld16(tbase + s * p.n_tile + c0, r);
+          for (int s0 = 0; s0 < nsub; s0 += 2) {
+            uint32_t r[2][16];
+            tmem_ld16(tbase + s0 * p.n_tile + c0, r[0]);
+            if (s0 + 1 < nsub) tmem_ld16(tbase + (s0 + 1) * p.n_tile + c0, r[1]);
             tmem_ld_wait();
-            float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float a = 0.f;
-              if (valid && cb + i < p.e.cout_store) {
-                a = __uint_as_float(r[i]) + __ldg(p.e.bias + cb + i);
-                a = apply_act(a, p.e.act);
-                if (p.e.post_scale) a = a * __ldg(p.e.post_scale + cb + i) + __ldg(p.e.post_shift + cb + i);
+            for (int u = 0; u < 2; ++u) {
+              if (s0 + u < nsub) {
+                const int py = ty * p.tr + (s0 + u) * p.sr + mr;
+                const bool valid = (py < p.g.H) && (px < p.g.W);
+                const size_t pix = ((size_t)n * p.g.H + py) * p.g.W + px;
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = apply_act(__uint_as_float(r[u][i]) + bias[i], p.e.act);
+                if (has_post) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], c_scale[cb + i], c_shift[cb + i]);
+                }
+                if (valid) store16(p.e.out_hi, p.e.out_lo, pix * p.e.out_C + p.e.out_coff + cb, v);
+                if (p.e.stats) {
+                  const float mk = valid ? 1.f : 0.f;
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    const float w = v[i] * mk;
+                    sacc[i] += w;
+                    sacc[16 + i] = fmaf(w, w, sacc[16 + i]);
+                  }
+                }
               }
-              v[i] = a;
-            }
-            if (valid) {
-              if (cb + 8 <= p.e.cout_store) store8(p.e.out_hi, p.e.out_lo, pix * p.e.out_C + p.e.out_coff + cb, v);
-              if (cb + 16 <= p.e.cout_store) store8(p.e.out_hi, p.e.out_lo, pix * p.e.out_C + p.e.out_coff + cb + 8, v + 8);
-            }
-            if (p.e.stats) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) { sacc[i] += v[i]; sacc[16 + i] = fmaf(v[i], v[i], sacc[16 + i]); }
             }
           }
           if (p.e.stats) {
@@ -418,8 +502,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             if (quarter == 0) {
               const float t4 = sb[lane] + sb[32 + lane] + sb[64 + lane] + sb[96 + lane];
               const int ch = cb + (lane & 15);
-              if (ch < p.e.cout_store)
-                atomicAdd(p.e.stats + ((size_t)n * p.e.stats_C + p.e.stats_coff + ch) * 2 + (lane >> 4), (double)t4);
+              atomicAdd(p.e.stats + ((size_t)n * p.e.stats_C + p.e.stats_coff + ch) * 2 + (lane >> 4), (double)t4);
             }
             ++stat_flip;
           }
@@ -431,26 +514,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const bool valid = (py < p.g.H) && (px < p.g.W);
           const size_t pix = ((size_t)n * p.g.H + py) * p.g.W + px;
           float s0 = 0.f, s1 = 0.f;
+#pragma unroll
           for (int c0 = 0; c0 < 32; c0 += 16) {
             uint32_t r0[16], r1[16], r2[16];
             tmem_ld16(tbase + (s * 3 + 0) * 32 + c0, r0);
             tmem_ld16(tbase + (s * 3 + 1) * 32 + c0, r1);
             tmem_ld16(tbase + (s * 3 + 2) * 32 + c0, r2);
-            tmem_ld_wait();
-            if (valid) {
-              float o[16];
-              load8(p.e.o_hi, p.e.o_lo, pix * 32 + c0, o);
-              load8(p.e.o_hi, p.e.o_lo, pix * 32 + c0 + 8, o + 8);
+            float o[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int ch = c0 + i;
-                float v = o[i];
-                v += fmaxf(__uint_as_float(r0[i]) + __ldg(p.e.bias + ch), 0.f);
-                v += fmaxf(__uint_as_float(r1[i]) + __ldg(p.e.bias + p.g.cout_pad + ch), 0.f);
-                v += fmaxf(__uint_as_float(r2[i]) + __ldg(p.e.bias + 2 * p.g.cout_pad + ch), 0.f);
-                s0 += v * __ldg(p.e.score_w + ch);
-                s1 += v * __ldg(p.e.score_w + 32 + ch);
-              }
+            for (int i = 0; i < 16; ++i) o[i] = 0.f;
+            if (valid) load16(p.e.o_hi, p.e.o_lo, pix * 32 + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int ch = c0 + i;
+              float v = o[i];
+              v += fmaxf(__uint_as_float(r0[i]) + c_bias[ch], 0.f);
+              v += fmaxf(__uint_as_float(r1[i]) + c_bias[p.g.cout_pad + ch], 0.f);
+              v += fmaxf(__uint_as_float(r2[i]) + c_bias[2 * p.g.cout_pad + ch], 0.f);
+              s0 = fmaf(v, c_scale[ch], s0);
+              s1 = fmaf(v, c_scale[32 + ch], s1);
             }
           }
           if (valid) {
@@ -528,7 +611,7 @@ static void make_w_map(CUtensorMap* map, const bf16* ptr, int rows, int kpad, in
 static size_t tc_smem_bytes(const TcParams& p) {
   const int nplanes = p.nsplit == 1 ? 1 : 2;
   return 1024 + (size_t)p.na * nplanes * p.a_plane_bytes + (size_t)p.nw * nplanes * p.w_plane_bytes +
-         8 * (2 * p.na + 2 * p.nw + 4) + 16 + 2 * 2 * 4 * 32 * sizeof(float);
+         8 * (2 * p.na + 2 * p.nw + 4) + 16 + (2 * 2 * 4 * 32 + 768 + 512 + 512) * sizeof(float);
 }
 
 // Fills the tiling fields of `p` from the geometry (taps must be sorted by dx) and sizes the rings.
@@ -548,10 +631,12 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   EGN_CHECK(cols <= 512, "accumulator groups exceed TMEM");
   // more sub-tiles per CTA tile amortise the weight stream and give the MMA pipe independent
   // accumulators to interleave; prefer shapes that keep two TMEM buffers
+  // (measured: a second sub-tile that costs the double buffer loses ~15 % on N = 256 layers)
   p.S = 1;
   const int rows_avail = ceil_div(g.H, p.sr);
-  if (rows_avail >= 2 && 2 * cols <= 512) p.S = 2;
+  if (rows_avail >= 2 && 2 * cols <= TC_ACC_STRIDE) p.S = 2;
   if (rows_avail >= 4 && 4 * cols <= TC_ACC_STRIDE) p.S = 4;
+  if (const char* e = getenv("EGN_TC_SMAX")) p.S = std::min(p.S, std::max(1, atoi(e)));   // tuning knob
   p.tr = p.S * p.sr;
   p.acc_bufs = p.S * cols <= TC_ACC_STRIDE ? 2 : 1;
   p.tiles_x = ceil_div(g.W, bw);
@@ -573,11 +658,16 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
     ++p.aload_ntaps[p.n_aloads - 1];
   }
   p.box_rows = p.tr + 2 * p.dmax;
+  p.l2_prefetch = p.n_blocks == 1 ? 1 : 0;
+  p.l2_prefetch = 0;
+  if (const char* e = getenv("EGN_TC_PREFETCH")) p.l2_prefetch = atoi(e);
+  p.dbg = 0;
+  if (const char* e = getenv("EGN_TC_DBG")) p.dbg = atoi(e);
   p.a_box_bytes = (uint32_t)p.box_rows * bw * 64u;
   p.a_plane_bytes = (p.a_box_bytes + 1023u) & ~1023u;
   p.w_plane_bytes = (uint32_t)p.n_tile * 64u;
   const int nplanes = nsplit == 1 ? 1 : 2;
-  const size_t budget = 227 * 1024 - 1024 - 512 - 2048;
+  const size_t budget = 227 * 1024 - 1024 - 512 - 2048 - 7168;
   const size_t a_slot = (size_t)nplanes * p.a_plane_bytes, w_slot = (size_t)nplanes * p.w_plane_bytes;
   p.na = 2;
   EGN_CHECK(budget > p.na * a_slot + 2 * w_slot, "conv_tc: tile does not fit in shared memory");

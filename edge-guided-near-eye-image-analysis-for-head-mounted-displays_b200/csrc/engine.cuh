@@ -308,11 +308,11 @@ struct Engine {
                           const float* post_shift = nullptr) {
     L.e.mode = CONV_STORE;
     L.e.act = act;
-    L.e.cout_store = round_up(L.cout, 8);
+    L.e.cout_store = L.g.cout_pad;           // whole 16-channel groups: 32-byte stores in the epilogue
     L.e.out_hi = dst->hi; L.e.out_lo = dst->lo; L.e.out_C = dst->C; L.e.out_coff = coff;
     L.e.post_scale = post_scale; L.e.post_shift = post_shift;
     EGN_CHECK(dst->H == L.g.H && dst->W == L.g.W, L.name + ": destination size mismatch");
-    EGN_CHECK(coff % 8 == 0 && coff + L.e.cout_store <= dst->C, L.name + ": destination channel window");
+    EGN_CHECK(coff % 16 == 0 && dst->C % 16 == 0 && coff + L.e.cout_store <= dst->C, L.name + ": destination channel window");
   }
 
   void set_stats(ConvLayer& L, double* stats, int stats_C, int stats_coff) {
@@ -635,7 +635,7 @@ struct Engine {
     debug_acts["bt"] = {es.bt, {0, 153}};
     for (int i = 0; i < 5; ++i) {
       Block& b = es.blk[i];
-      b.in_c = in_c[i]; b.in_pad = round_up(in_c[i], 8); b.inter = inter[i]; b.op_c = op_c[i];
+      b.in_c = in_c[i]; b.in_pad = round_up(in_c[i], 16); b.inter = inter[i]; b.op_c = op_c[i];
       b.H = bh[i]; b.W = bw[i];
       b.off_out = 0; b.off_x = inter[i]; b.off_x1 = b.off_x + b.in_pad; b.off_x22 = b.off_x1 + inter[i];
       b.buf = new_act(mem, E, b.H, b.W, b.off_x22 + inter[i]);
@@ -729,11 +729,11 @@ struct Engine {
     for (int i = 0; i < 4; ++i) {
       UpBlock& u = es.up[i];
       Block& sk = es.blk[3 - i];
-      u.in_c = d_in[i]; u.out_c = d_out[i]; u.out_pad = round_up(d_out[i], 8);
+      u.in_c = d_in[i]; u.out_c = d_out[i]; u.out_pad = round_up(d_out[i], 16);
       // the upsampled input occupies [0, in_pad); with add_edge the first block's input is
       // cat(x, x_edge) (RITnet_v2.py:286) and each 153-channel half gets its own 8-aligned slot
       const bool two_halves = (i == 0 && cfg.add_edge);
-      u.in_pad = two_halves ? 2 * 160 : round_up(d_in[i], 8);
+      u.in_pad = two_halves ? 2 * 160 : round_up(d_in[i], 16);
       u.skip_c = sk.inter + sk.in_c; u.H = sk.H; u.W = sk.W;
       u.buf = new_act(mem, mb, u.H, u.W, u.in_pad + u.out_pad);
       u.t = new_act(mem, mb, u.H, u.W, u.out_pad);
