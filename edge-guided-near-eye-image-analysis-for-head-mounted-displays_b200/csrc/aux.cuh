@@ -332,16 +332,23 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const UpsampleParams p)
 
 // ------------------------------------------------------------------------------------------
 // Spatial mean of a channel window -> fp32 [B][Cs]  (latent, RITnet_v2.py:282).
+// Block per frame; blockDim.x = 4 * 160: four pixel quarters per channel, combined in shared memory.
 __global__ void spatial_mean_kernel(View src, float* out, int B, int HW, int Cs) {
+  __shared__ float part[4][160];
   const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
-    float s = 0.f;
-    for (int px = 0; px < HW; ++px) {
+  const int c = threadIdx.x % 160, qtr = threadIdx.x / 160;
+  float s = 0.f;
+  if (c < Cs) {
+    const int per = (HW + 3) / 4;
+    const int p1 = min(HW, (qtr + 1) * per);
+    for (int px = qtr * per; px < p1; ++px) {
       const size_t i = ((size_t)(n + src.n_off) * HW + px) * src.C + src.coff + c;
       s += join_bf16(src.hi[i], src.lo[i]);
     }
-    out[(size_t)n * Cs + c] = s / (float)HW;
   }
+  part[qtr][c] = s;
+  __syncthreads();
+  if (qtr == 0 && c < Cs) out[(size_t)n * Cs + c] = (part[0][c] + part[1][c] + part[2][c] + part[3][c]) / (float)HW;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -394,41 +401,170 @@ __global__ void bdcn_tail_kernel(const BdcnTailParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Regression head input: fp32 NHWC [B][15][20][Cf] gathered from the bottleneck windows
-// (image frames, then edge frames when add_edge) with the optional AdaIN transform
-// (RITnet_v2.py:280-308: unbiased variance + 1e-5).
-struct HeadInputParams {
+// AdaIN on the bottleneck before the regression head (RITnet_v2.py:297-308, 251-259: per
+// (frame, channel) mean / UNBIASED variance + 1e-5 over the 300 bottleneck pixels, then
+// gamma * x_hat + beta with the MLP's parameters).  Reads the image (and edge) bottleneck windows
+// and writes the transformed channels into the split-bf16 buffer the head's first convolution reads;
+// source s's channel c lands at dst channel s * Cslot + c.
+struct AdainApplyParams {
   View src[2];
-  int nsrc, Cs;            // channels per source (153)
-  const float* adain;      // [B][2][Cf] (gamma, beta) or null
-  float* out;              // [B][HW][Cf]
+  int nsrc, Cs, Cslot;
+  const float* adain;      // [B][2][Cf] (gamma, beta), Cf = nsrc * Cs
+  View dst;
   int B, HW;
 };
 
-__global__ void head_input_kernel(const HeadInputParams p) {
+__global__ void adain_apply_kernel(const AdainApplyParams p) {
   const int Cf = p.nsrc * p.Cs;
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < Cf; c += blockDim.x) {
     const View& s = p.src[c / p.Cs];
     const int cc = c % p.Cs;
-    float v[300];
+    const size_t base = (size_t)(n + s.n_off) * p.HW * s.C + s.coff + cc;
     float sum = 0.f;
+    for (int px = 0; px < p.HW; ++px) sum += join_bf16(s.hi[base + (size_t)px * s.C], s.lo[base + (size_t)px * s.C]);
+    const float mean = sum / p.HW;
+    float q = 0.f;
     for (int px = 0; px < p.HW; ++px) {
-      const size_t i = ((size_t)(n + s.n_off) * p.HW + px) * s.C + s.coff + cc;
-      v[px] = join_bf16(s.hi[i], s.lo[i]);
-      sum += v[px];
+      const float d = join_bf16(s.hi[base + (size_t)px * s.C], s.lo[base + (size_t)px * s.C]) - mean;
+      q = fmaf(d, d, q);
     }
-    float g = 1.f, b = 0.f, mean = 0.f, istd = 1.f;
-    if (p.adain) {
-      mean = sum / p.HW;
-      float q = 0.f;
-      for (int px = 0; px < p.HW; ++px) q += (v[px] - mean) * (v[px] - mean);
-      istd = 1.f / sqrtf(q / (p.HW - 1) + 1e-5f);
-      g = p.adain[((size_t)n * 2 + 0) * Cf + c];
-      b = p.adain[((size_t)n * 2 + 1) * Cf + c];
+    const float istd = 1.f / sqrtf(q / (p.HW - 1) + 1e-5f);
+    const float g = p.adain[((size_t)n * 2 + 0) * Cf + c], b = p.adain[((size_t)n * 2 + 1) * Cf + c];
+    const size_t ob = (size_t)(n + p.dst.n_off) * p.HW * p.dst.C + p.dst.coff + (c / p.Cs) * p.Cslot + cc;
+    for (int px = 0; px < p.HW; ++px) {
+      const float v = join_bf16(s.hi[base + (size_t)px * s.C], s.lo[base + (size_t)px * s.C]);
+      split_bf16((v - mean) * istd * g + b, p.dst.hi[ob + (size_t)px * p.dst.C], p.dst.lo[ob + (size_t)px * p.dst.C]);
     }
-    for (int px = 0; px < p.HW; ++px)
-      p.out[((size_t)n * p.HW + px) * Cf + c] = p.adain ? (v[px] - mean) * istd * g + b : v[px];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Regression head after its first convolution (utils.py:1013-1037): AvgPool2d(2) of the 14x18
+// valid region of c1's output -> c2 3x3 valid (128->128, bias, lrelu) -> c3 3x3 valid (128->32,
+// no bias, lrelu) -> flatten -> l1 (480->256, SELU) -> l2 (256->10) -> tanh / sigmoid split.
+// One CTA per frame keeps every intermediate in shared memory.
+struct HeadTailParams {
+  View c1;              // [B][15][20][128] lrelu(c1(x)), valid region 14 x 18
+  const float* w_c2;    // [3][3][128][128]  (kh, kw, ci, co)
+  const float* b_c2;    // [128]
+  const float* w_c3;    // [3][3][128][32]
+  const float* w_l1t;   // [480][256], input index = (y*5 + x)*32 + c
+  const float* b_l1;    // [256]
+  const float* w_l2;    // [10][256]
+  const float* b_l2;    // [10]
+  float* el_out;        // [B][10]
+  int B;
+};
+
+#define HEAD_TAIL_THREADS 256
+#define HEAD_TAIL_SMEM ((63 * 128 + 35 * 128) * sizeof(float))
+
+__global__ void __launch_bounds__(HEAD_TAIL_THREADS) head_tail_kernel(const HeadTailParams p) {
+  extern __shared__ float ht_sm[];
+  float* p1 = ht_sm;                  // [7*9][128] pooled c1
+  float* c2o = ht_sm + 63 * 128;      // [5*7][128]
+  float* c3o = p1;                    // [3*5][32]   (p1 is dead once c2 is done)
+  float* l1o = p1 + 512;              // [256]
+  const int n = blockIdx.x, t = threadIdx.x;
+  // ---- AvgPool2d(2) (utils.py:990) of the valid 14x18 region
+  for (int i = t; i < 63 * 16; i += HEAD_TAIL_THREADS) {
+    const int g8 = i & 15, pix = i >> 4;
+    const int py = pix / 9, px = pix % 9;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        float v[8];
+        load8(p.c1.hi, p.c1.lo, ((size_t)(n + p.c1.n_off) * 300 + (size_t)(2 * py + r) * 20 + 2 * px + s) * p.c1.C + p.c1.coff + g8 * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += v[k];
+      }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) p1[pix * 128 + g8 * 8 + k] = 0.25f * acc[k];
+  }
+  __syncthreads();
+  // ---- c2: thread = (output channel, pixel parity); 18 pixels per thread
+  {
+    const int co = t & 127, half = t >> 7;
+    float acc[18];
+    int off[18];
+    const float bias = p.b_c2[co];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      const int q = min(half + 2 * i, 34);
+      acc[i] = bias;
+      off[i] = ((q / 7) * 9 + q % 7) * 128;
+    }
+    for (int tap = 0; tap < 9; ++tap) {
+      const int toff = ((tap / 3) * 9 + tap % 3) * 128;
+      const float* w = p.w_c2 + (size_t)tap * 128 * 128 + co;
+      for (int ci = 0; ci < 128; ci += 4) {
+        const float w0 = __ldg(w + (size_t)ci * 128), w1 = __ldg(w + (size_t)(ci + 1) * 128);
+        const float w2 = __ldg(w + (size_t)(ci + 2) * 128), w3 = __ldg(w + (size_t)(ci + 3) * 128);
+#pragma unroll
+        for (int i = 0; i < 18; ++i) {
+          const float4 a = *reinterpret_cast<const float4*>(p1 + off[i] + toff + ci);
+          acc[i] = fmaf(a.x, w0, fmaf(a.y, w1, fmaf(a.z, w2, fmaf(a.w, w3, acc[i]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      const int q = half + 2 * i;
+      if (q < 35) c2o[q * 128 + co] = apply_act(acc[i], ACT_LRELU);
+    }
+  }
+  __syncthreads();
+  // ---- c3: thread = (output channel, pixel group); pixels pg and pg + 8 of the 3x5 map
+  {
+    const int co = t & 31, pg = t >> 5;
+    const int q0 = pg, q1 = min(pg + 8, 14);
+    const int o0 = ((q0 / 5) * 7 + q0 % 5) * 128, o1 = ((q1 / 5) * 7 + q1 % 5) * 128;
+    float a0 = 0.f, a1 = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int toff = ((tap / 3) * 7 + tap % 3) * 128;
+      const float* w = p.w_c3 + (size_t)tap * 128 * 32 + co;
+#pragma unroll 4
+      for (int ci = 0; ci < 128; ci += 4) {
+        const float w0 = __ldg(w + ci * 32), w1 = __ldg(w + (ci + 1) * 32), w2 = __ldg(w + (ci + 2) * 32), w3 = __ldg(w + (ci + 3) * 32);
+        const float4 x0 = *reinterpret_cast<const float4*>(c2o + o0 + toff + ci);
+        const float4 x1 = *reinterpret_cast<const float4*>(c2o + o1 + toff + ci);
+        a0 = fmaf(x0.x, w0, fmaf(x0.y, w1, fmaf(x0.z, w2, fmaf(x0.w, w3, a0))));
+        a1 = fmaf(x1.x, w0, fmaf(x1.y, w1, fmaf(x1.z, w2, fmaf(x1.w, w3, a1))));
+      }
+    }
+    c3o[q0 * 32 + co] = apply_act(a0, ACT_LRELU);
+    if (pg + 8 < 15) c3o[(pg + 8) * 32 + co] = apply_act(a1, ACT_LRELU);
+  }
+  __syncthreads();
+  // ---- l1 + SELU (utils.py:1021)
+  {
+    float acc = p.b_l1[t];
+#pragma unroll 8
+    for (int i = 0; i < 480; ++i) acc = fmaf(c3o[i], __ldg(p.w_l1t + (size_t)i * 256 + t), acc);
+    const float alpha = 1.6732632423543772848170429916717f, scale = 1.0507009873554804934193349852946f;
+    l1o[t] = scale * (acc > 0.f ? acc : alpha * (expf(acc) - 1.f));
+  }
+  __syncthreads();
+  // ---- l2 + the ellipse split (utils.py:1022-1036): one warp per output
+  for (int o = t >> 5; o < 10; o += HEAD_TAIL_THREADS / 32) {
+    const int lane = t & 31;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc = fmaf(l1o[lane + 32 * i], __ldg(p.w_l2 + o * 256 + lane + 32 * i), acc);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) {
+      acc += p.b_l2[o];
+      const int k = o % 5;
+      if (k < 2) acc = tanhf(acc);
+      else if (k < 4) acc = 1.f / (1.f + expf(-acc));
+      p.el_out[(size_t)n * 10 + o] = acc;
+    }
   }
 }
 

@@ -173,8 +173,9 @@ struct Engine {
     LastConvParams last;
     // regression head + AdaIN (fp32)
     int Cf = 0;
-    float *hin, *c1o, *p1o, *c2o, *c3o, *l1o;
-    float *w_c1, *b_c1, *w_c2, *b_c2, *w_c3, *w_l1, *b_l1, *w_l2, *b_l2;
+    Act *hin, *c1o;               // AdaIN-transformed head input (add_seg only); lrelu(c1(x))
+    ConvLayer head_c1;
+    HeadTailParams head;
     float *sm, *se[5], *gap, *sty, *m1, *m2, *adain;
     float *w_se[5], *b_se[5], *w_se6, *b_se6, *w_m[3], *b_m[3];
     float* logits_tmp;
@@ -352,16 +353,22 @@ struct Engine {
     if (profiling) profile_end(st, L.flops * batch, &L, nullptr, batch);
   }
 
-  void run_conv_impl(ConvLayer& L, int batch, cudaStream_t st) {
+  // noff >= 0 re-bases every K chunk that reads a frame-offset window (the edge frames of the
+  // shared encoder sit at [nb, 2nb) of its buffers, and nb shrinks on a ragged last micro-batch)
+  void run_conv_impl(ConvLayer& L, int batch, cudaStream_t st, int noff = -1) {
     if (use_tc) {
       TcParams p = L.tc;
       p.g.batch = batch;
+      if (noff >= 0)
+        for (int c = 0; c < p.g.nchunks; ++c) if (p.g.chunk_noff[c]) p.g.chunk_noff[c] = noff;
       p.total_tiles = p.tiles_x * p.tiles_y * batch * p.n_blocks;
       tc_launch(p, num_sms, st);
       ++launches;
     } else {
       SimtParams p = L.simt;
       p.g.batch = batch;
+      if (noff >= 0)
+        for (int c = 0; c < p.g.nchunks; ++c) if (p.g.chunk_noff[c]) p.g.chunk_noff[c] = noff;
       simt_launch(p, st);
       ++launches;
     }
@@ -793,27 +800,44 @@ struct Engine {
     // regression head (utils.py:983-1037), fp32
     const int Cf = 153 * (cfg.add_edge ? 2 : 1);
     es.Cf = Cf;
-    es.hin = (float*)mem.alloc((size_t)mb * 300 * Cf * 4);
-    es.c1o = (float*)mem.alloc((size_t)mb * 14 * 18 * 128 * 4);
-    es.p1o = (float*)mem.alloc((size_t)mb * 7 * 9 * 128 * 4);
-    es.c2o = (float*)mem.alloc((size_t)mb * 5 * 7 * 128 * 4);
-    es.c3o = (float*)mem.alloc((size_t)mb * 3 * 5 * 32 * 4);
-    es.l1o = (float*)mem.alloc((size_t)mb * 256 * 4);
-    es.w_c1 = upload_hwio(mem, sd_get(sd, "elReg.c1.weight")); es.b_c1 = mem.upload(sd_get(sd, "elReg.c1.bias").data);
-    es.w_c2 = upload_hwio(mem, sd_get(sd, "elReg.c2.weight")); es.b_c2 = mem.upload(sd_get(sd, "elReg.c2.bias").data);
-    es.w_c3 = upload_hwio(mem, sd_get(sd, "elReg.c3.weight"));
+    // c1 (2x3, valid) runs on the tensor cores as a "same"-geometry convolution over the 15x20 grid
+    // whose outputs beyond the valid 14x18 region are never read; the rest of the head is one
+    // fused SIMT kernel per frame (aux.cuh head_tail_kernel)
     EGN_CHECK(sd_get(sd, "elReg.c1.weight").shape[1] == Cf, "elReg.c1 input channels do not match the setting");
+    es.c1o = new_act(mem, mb, 15, 20, 128);
+    es.hin = cfg.add_seg ? new_act(mem, mb, 15, 20, cfg.add_edge ? 320 : 160) : nullptr;
     {
-      // l1 consumes the NCHW flatten c*15 + y*5 + x (utils.py:1020); our c3 output is NHWC
+      std::vector<Piece> hp;
+      if (cfg.add_seg) {
+        hp.push_back({es.hin, 0, 153, 0});
+        if (cfg.add_edge) hp.push_back({es.hin, 160, 153, 0});
+      } else {
+        hp.push_back({es.bt, 0, 153, 0});
+        if (cfg.add_edge) hp.push_back({es.bt, 0, 153, mb});      // edge frames: offset patched per launch
+      }
+      const HostTensor& w = sd_get(sd, "elReg.c1.weight");
+      const HostTensor& b = sd_get(sd, "elReg.c1.bias");
+      build_conv(es.head_c1, mem, "elReg.c1", hp, {{w.data.data(), b.data.data(), 1, 0}}, 128, Cf, 2, 3, 15, 20, mb);
+      set_store_epilogue(es.head_c1, es.c1o, 0, ACT_LRELU);
+      es.head_c1.flops = 2.0 * 128 * Cf * 6 * 14 * 18;
+      finalize_conv(es.head_c1);
+    }
+    {
+      HeadTailParams& h = es.head;
+      h.c1 = make_view(*es.c1o, 0);
+      h.w_c2 = upload_hwio(mem, sd_get(sd, "elReg.c2.weight")); h.b_c2 = mem.upload(sd_get(sd, "elReg.c2.bias").data);
+      h.w_c3 = upload_hwio(mem, sd_get(sd, "elReg.c3.weight"));
+      // l1 consumes the NCHW flatten c*15 + y*5 + x (utils.py:1020); c3's output here is NHWC, and the
+      // matrix is stored input-major so consecutive threads read consecutive outputs
       const HostTensor& w = sd_get(sd, "elReg.l1.weight");
-      std::vector<float> wp(256 * 480);
+      std::vector<float> wt(480 * 256);
       for (int o = 0; o < 256; ++o)
         for (int c = 0; c < 32; ++c)
-          for (int px = 0; px < 15; ++px) wp[(size_t)o * 480 + px * 32 + c] = w.data[(size_t)o * 480 + c * 15 + px];
-      es.w_l1 = mem.upload(wp);
-      es.b_l1 = mem.upload(sd_get(sd, "elReg.l1.bias").data);
-      es.w_l2 = mem.upload(sd_get(sd, "elReg.l2.weight").data);
-      es.b_l2 = mem.upload(sd_get(sd, "elReg.l2.bias").data);
+          for (int px = 0; px < 15; ++px) wt[(size_t)(px * 32 + c) * 256 + o] = w.data[(size_t)o * 480 + c * 15 + px];
+      h.w_l1t = mem.upload(wt);
+      h.b_l1 = mem.upload(sd_get(sd, "elReg.l1.bias").data);
+      h.w_l2 = mem.upload(sd_get(sd, "elReg.l2.weight").data);
+      h.b_l2 = mem.upload(sd_get(sd, "elReg.l2.bias").data);
     }
     es.adain = nullptr;
     if (cfg.add_seg) {
@@ -913,7 +937,7 @@ struct Engine {
       }
       // with add_edge the edge frames sit at [nb, 2nb) of every encoder buffer
       const int eoff = nb;
-      spatial_mean_kernel<<<nb, 160, 0, st>>>(make_view(*es.bt, 0, 0), latent + (size_t)b0 * 153, nb, 300, 153);
+      spatial_mean_kernel<<<nb, 640, 0, st>>>(make_view(*es.bt, 0, 0), latent + (size_t)b0 * 153, nb, 300, 153);
       CUDA_OK(cudaGetLastError()); ++launches;
       // ---- decoder
       for (int i = 0; i < 4; ++i) {
@@ -963,21 +987,24 @@ struct Engine {
       }
       // ---- regression head
       if (profiling) { if (prof_used >= 8192) profile_resolve(); profile_begin(st); }
-      HeadInputParams hp;
-      hp.src[0] = make_view(*es.bt, 0, 0); hp.src[1] = make_view(*es.bt, 0, eoff);
-      hp.nsrc = cfg.add_edge ? 2 : 1; hp.Cs = 153; hp.adain = cfg.add_seg ? es.adain : nullptr;
-      hp.out = es.hin; hp.B = nb; hp.HW = 300;
-      head_input_kernel<<<nb, 320, 0, st>>>(hp); CUDA_OK(cudaGetLastError()); ++launches;
-      conv_f32(es.hin, es.w_c1, es.b_c1, es.c1o, nb, 15, 20, es.Cf, 128, 2, 3, 1, 0, ACT_LRELU, 0, st);
-      {
-        const long long total = (long long)nb * 7 * 9 * 128;
-        avgpool_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(es.c1o, es.p1o, nb, 14, 18, 128);
-        CUDA_OK(cudaGetLastError()); ++launches;
+      if (cfg.add_seg) {
+        AdainApplyParams ap;
+        ap.src[0] = make_view(*es.bt, 0, 0); ap.src[1] = make_view(*es.bt, 0, eoff);
+        ap.nsrc = cfg.add_edge ? 2 : 1; ap.Cs = 153; ap.Cslot = 160; ap.adain = es.adain;
+        ap.dst = make_view(*es.hin, 0); ap.B = nb; ap.HW = 300;
+        adain_apply_kernel<<<nb, 320, 0, st>>>(ap); CUDA_OK(cudaGetLastError()); ++launches;
       }
-      conv_f32(es.p1o, es.w_c2, es.b_c2, es.c2o, nb, 7, 9, 128, 128, 3, 3, 1, 0, ACT_LRELU, 0, st);
-      conv_f32(es.c2o, es.w_c3, nullptr, es.c3o, nb, 5, 7, 128, 32, 3, 3, 1, 0, ACT_LRELU, 0, st);
-      linear(es.c3o, es.w_l1, es.b_l1, es.l1o, nb, 480, 256, 3, st);
-      linear(es.l1o, es.w_l2, es.b_l2, el_out + (size_t)b0 * 10, nb, 256, 10, 4, st);
+      run_conv_impl(es.head_c1, nb, st, cfg.add_seg ? -1 : eoff);
+      {
+        static bool attr_set = false;
+        if (!attr_set) {
+          CUDA_OK(cudaFuncSetAttribute(head_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_TAIL_SMEM));
+          attr_set = true;
+        }
+        HeadTailParams h = es.head;
+        h.B = nb; h.el_out = el_out + (size_t)b0 * 10;
+        head_tail_kernel<<<nb, HEAD_TAIL_THREADS, HEAD_TAIL_SMEM, st>>>(h); CUDA_OK(cudaGetLastError()); ++launches;
+      }
       if (profiling) profile_end(st, 0, nullptr, "esf.reg_head", 0);
     }
   }
