@@ -22,6 +22,8 @@
 //   tmem_full/tmem_empty couple MMA and epilogue (two accumulator buffers when they fit in the
 //   512 TMEM columns); persistent CTAs stride over the tile list.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 #define TC_MAX_ALOADS 8
@@ -35,15 +37,27 @@ struct TcParams {
   int n_tile, n_blocks, tiles_x, tiles_y, total_tiles;
   int bw_log2, sr, S, tr, dmax, box_rows;
   int na, nw;                          // A / W ring depths
+  int wide_b;                          // 1: hi*hi and hi*lo issue as ONE MMA of N = 2*n_tile against the stacked [W_hi; W_lo] tile (A_hi read once)
+  int w_box;                           // 1: a W slot holds every tap of an activation box (one barrier round trip per box)
+  int w_slot_taps;                     // taps per W slot (1 unless w_box)
   uint32_t a_plane_bytes, a_box_bytes, w_plane_bytes;
   int acc_bufs;                        // TMEM accumulator buffers (1 or 2)
   int n_aloads;
   int l2_prefetch;                     // producer prefetches its next tile's activation boxes into L2
-  int dbg;                             // timing experiments only: 1 = skip epilogue body, 2 = skip MMAs, 4 = skip TMA loads
+  int dbg;                             // timing experiments only: 1 = skip epilogue body, 2 = skip MMAs, 4 = skip activation TMA loads, 8 = skip weight TMA loads
   int8_t aload_dx[TC_MAX_ALOADS];
   uint8_t aload_tap0[TC_MAX_ALOADS], aload_ntaps[TC_MAX_ALOADS];
   int* err_flag;
+  long long* timing;                   // optional [grid][10] cycle counters (EGN_TC_TIMING), see tc_launch
 };
+
+// Per-tap / per-chunk / per-box schedule entries, staged in shared memory once per CTA so the
+// single-thread producer and MMA issuer never index kernel parameters dynamically (an indexed
+// constant-bank load costs hundreds of cycles on the issue path).
+struct TcTapStep { uint32_t a_off, d_col, flags, pad; };   // flags: 1 first tap of its box, 2 last tap of its box, 4 first tap of its accumulator group
+struct TcChunk { int src, c0, noff, pad; };
+struct TcLoad { int dx, tap0, ntaps, pad; };
+#define TC_SCHED_BYTES (32 * 16 + EGN_MAX_CHUNKS * 16 + TC_MAX_ALOADS * 16)
 
 #define TC_THREADS 320
 #define TC_EPI_WARPS 8
@@ -69,7 +83,20 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 
 // Bounded wait: a protocol bug must surface as a trap, never as a hung GPU.
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+  if (mbar_try(bar, parity)) return;              // common case: no clock read, no loop
   uint32_t done = 0;
   const long long t0 = clock64();
   for (;;) {
@@ -175,25 +202,36 @@ __device__ __forceinline__ bool elect_one() {
 
 // All MMAs of one (chunk, tap): NSUB sub-tiles x 2 K-steps x (1 or 3) split products, ordered so
 // that consecutive instructions target different accumulators.
-template <int NSUB, int NPL>
+template <int NSUB, int NPL, int WIDE>
 __device__ __forceinline__ void issue_tap(uint32_t sA, uint32_t a_plane, uint32_t sW, uint32_t w_plane,
-                                          uint32_t d_tmem, uint32_t sub_cols, uint32_t idesc, uint32_t first) {
+                                          uint32_t d_tmem, uint32_t sub_cols, uint32_t idesc, uint32_t idesc_wide,
+                                          uint32_t first) {
   const uint64_t dA_hi = make_desc(sA), dW_hi = make_desc(sW);
   const uint64_t dA_lo = make_desc(sA + a_plane), dW_lo = make_desc(sW + w_plane);
 #pragma unroll
   for (int k = 0; k < EGN_KC / 16; ++k) {
     const uint64_t koff = (uint64_t)((k * 32) >> 4);        // 16 bf16 = 32 bytes along K
     const uint32_t acc = (k == 0) ? (first ^ 1u) : 1u;
+    if (NPL == 2 && WIDE) {
+      // A_hi x [W_hi; W_lo] -> columns [0, n) += hi*hi, [n, 2n) += hi*lo ; A_lo x W_hi -> columns [0, n)
 #pragma unroll
-    for (int s = 0; s < NSUB; ++s)
-      mma_bf16(d_tmem + s * sub_cols, dA_hi + koff + (uint64_t)(s * (8192 >> 4)), dW_hi + koff, idesc, acc);
-    if (NPL == 2) {
+      for (int s = 0; s < NSUB; ++s)
+        mma_bf16(d_tmem + s * sub_cols, dA_hi + koff + (uint64_t)(s * (8192 >> 4)), dW_hi + koff, idesc_wide, acc);
 #pragma unroll
       for (int s = 0; s < NSUB; ++s)
         mma_bf16(d_tmem + s * sub_cols, dA_lo + koff + (uint64_t)(s * (8192 >> 4)), dW_hi + koff, idesc, 1u);
+    } else {
 #pragma unroll
       for (int s = 0; s < NSUB; ++s)
-        mma_bf16(d_tmem + s * sub_cols, dA_hi + koff + (uint64_t)(s * (8192 >> 4)), dW_lo + koff, idesc, 1u);
+        mma_bf16(d_tmem + s * sub_cols, dA_hi + koff + (uint64_t)(s * (8192 >> 4)), dW_hi + koff, idesc, acc);
+      if (NPL == 2) {
+#pragma unroll
+        for (int s = 0; s < NSUB; ++s)
+          mma_bf16(d_tmem + s * sub_cols, dA_lo + koff + (uint64_t)(s * (8192 >> 4)), dW_hi + koff, idesc, 1u);
+#pragma unroll
+        for (int s = 0; s < NSUB; ++s)
+          mma_bf16(d_tmem + s * sub_cols, dA_hi + koff + (uint64_t)(s * (8192 >> 4)), dW_lo + koff, idesc, 1u);
+      }
     }
   }
 }
@@ -256,11 +294,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t base = (raw_addr + 1023u) & ~1023u;      // swizzled tiles: 1024-B aligned slots
   uint8_t* smem = smem_raw + (base - raw_addr);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform by construction
   const int lane = threadIdx.x & 31;
   const int nplanes = p.nsplit == 1 ? 1 : 2;
   const uint32_t a_slot_bytes = nplanes * p.a_plane_bytes;
-  const uint32_t w_slot_bytes = nplanes * p.w_plane_bytes;
+  const uint32_t w_tap_bytes = nplanes * p.w_plane_bytes;
+  const uint32_t w_slot_bytes = p.w_slot_taps * w_tap_bytes;
   const int na = p.na, nw = p.nw;
 
   const uint32_t w_base = base + na * a_slot_bytes;
@@ -295,6 +334,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   float* c_bias = stat_buf + 2 * 2 * 4 * 32;       // [groups * cout_pad] <= 768
   float* c_scale = c_bias + 768;                   // [cout_pad] <= 512   (MSBlock: score_w[64])
   float* c_shift = c_scale + 512;                  // [cout_pad] <= 512
+  TcTapStep* s_tap = reinterpret_cast<TcTapStep*>(c_shift + 512);
+  TcChunk* s_chunk = reinterpret_cast<TcChunk*>(s_tap + 32);
+  TcLoad* s_load = reinterpret_cast<TcLoad*>(s_chunk + EGN_MAX_CHUNKS);
+  if ((int)threadIdx.x < p.g.ntaps) {
+    const int t = threadIdx.x;
+    TcTapStep st;
+    st.a_off = (uint32_t)((p.g.tap_dy[t] + p.dmax) << p.bw_log2) * 64u;
+    st.d_col = (uint32_t)(p.g.tap_grp[t] * p.n_tile * (p.wide_b ? 2 : 1));
+    st.flags = 0; st.pad = 0;
+    for (int l = 0; l < p.n_aloads; ++l) {
+      if (t == p.aload_tap0[l]) st.flags |= 1u;
+      if (t == p.aload_tap0[l] + p.aload_ntaps[l] - 1) st.flags |= 2u;
+    }
+    bool seen = false;
+    for (int u = 0; u < t; ++u) seen |= (p.g.tap_grp[u] == p.g.tap_grp[t]);
+    if (!seen) st.flags |= 4u;
+    s_tap[t] = st;
+  }
+  if ((int)threadIdx.x >= 64 && (int)threadIdx.x < 64 + p.g.nchunks) {
+    const int c = threadIdx.x - 64;
+    s_chunk[c] = TcChunk{(int)p.g.chunk_src[c], (int)p.g.chunk_c0[c], p.g.chunk_noff[c], 0};
+  }
+  if ((int)threadIdx.x >= 128 && (int)threadIdx.x < 128 + p.n_aloads) {
+    const int l = threadIdx.x - 128;
+    s_load[l] = TcLoad{(int)p.aload_dx[l], (int)p.aload_tap0[l], (int)p.aload_ntaps[l], 0};
+  }
   for (int i = threadIdx.x; i < p.g.groups * p.g.cout_pad; i += blockDim.x) c_bias[i] = p.e.bias[i];
   if (p.e.post_scale)
     for (int i = threadIdx.x; i < p.g.cout_pad; i += blockDim.x) { c_scale[i] = p.e.post_scale[i]; c_shift[i] = p.e.post_shift[i]; }
@@ -311,115 +376,228 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (lane == 0) {
       int as = 0, ws = 0;
       uint32_t aph = 0, wph = 0;
+      const int nchunks = p.g.nchunks, n_aloads = p.n_aloads, n_blocks = p.n_blocks, tiles_x = p.tiles_x, tiles_y = p.tiles_y;
+      const uint32_t a_tx = nplanes * p.a_box_bytes, w_tx = nplanes * p.w_plane_bytes;
+      const uint32_t a_plane = p.a_plane_bytes, w_plane = p.w_plane_bytes;
+      const int cout_pad = p.g.cout_pad, n_tile = p.n_tile, dbg = p.dbg;
+      const bool ptm = p.timing != nullptr;
+      long long ptm_a = 0, ptm_w = 0, ptm_c0 = 0;
+      const long long ptm_start = ptm ? clock64() : 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nb = tile % p.n_blocks;
-        int rest = tile / p.n_blocks;
-        const int tx = rest % p.tiles_x;
-        rest /= p.tiles_x;
-        const int ty = rest % p.tiles_y;
-        const int n = rest / p.tiles_y;
+        const int nb = tile % n_blocks;
+        int rest = tile / n_blocks;
+        const int tx = rest % tiles_x;
+        rest /= tiles_x;
+        const int ty = rest % tiles_y;
+        const int n = rest / tiles_y;
         const int x0 = tx * bw;
         const int y0 = ty * p.tr - p.dmax;
-        // the activations stream from HBM: pull this CTA's next tile into L2 while this one computes,
-        // so the ring's loads see L2 latency instead of DRAM latency (one box per chunk covers all dx
-        // but the outermost pixel columns)
-        if (p.l2_prefetch && nb == 0) {
-          const int nt = tile + gridDim.x * p.n_blocks;   // same nb, next spatial tile of this CTA
-          if (nt < p.total_tiles) {
-            int r2 = nt / p.n_blocks;
-            const int ptx = r2 % p.tiles_x;
-            r2 /= p.tiles_x;
-            const int pty = r2 % p.tiles_y;
-            const int pn = r2 / p.tiles_y;
-            for (int c = 0; c < p.g.nchunks; ++c) {
-              const int src = p.g.chunk_src[c];
-              tma_prefetch_4d(&p.a_map[0][src], p.g.chunk_c0[c], ptx * bw, pty * p.tr - p.dmax, pn + p.g.chunk_noff[c]);
-              if (nplanes == 2)
-                tma_prefetch_4d(&p.a_map[1][src], p.g.chunk_c0[c], ptx * bw, pty * p.tr - p.dmax, pn + p.g.chunk_noff[c]);
-            }
-          }
-        }
-        for (int c = 0; c < p.g.nchunks; ++c) {
-          const int src = p.g.chunk_src[c];
-          const int c0 = p.g.chunk_c0[c];
-          const int nn = n + p.g.chunk_noff[c];
-          for (int l = 0; l < p.n_aloads; ++l) {
+        const int wrow0 = nb * n_tile;
+        for (int c = 0; c < nchunks; ++c) {
+          const TcChunk ck = s_chunk[c];
+          const int nn = n + ck.noff;
+          const CUtensorMap* map_hi = &p.a_map[0][ck.src];
+          const CUtensorMap* map_lo = &p.a_map[1][ck.src];
+          for (int l = 0; l < n_aloads; ++l) {
+            const TcLoad ld = s_load[l];
+            if (ptm) ptm_c0 = clock64();
             mbar_wait(a_empty(as), aph ^ 1u, p.err_flag, 1);
-            mbar_expect_tx(a_full(as), nplanes * p.a_box_bytes);
+            if (ptm) ptm_a += clock64() - ptm_c0;
             const uint32_t sA = base + as * a_slot_bytes;
-            tma_load_4d(&p.a_map[0][src], a_full(as), sA, c0, x0 + p.aload_dx[l], y0, nn);
-            if (nplanes == 2)
-              tma_load_4d(&p.a_map[1][src], a_full(as), sA + p.a_plane_bytes, c0, x0 + p.aload_dx[l], y0, nn);
+            if (dbg & 4) {
+              mbar_arrive(a_full(as));
+            } else {
+              mbar_expect_tx(a_full(as), a_tx);
+              tma_load_4d(map_hi, a_full(as), sA, ck.c0, x0 + ld.dx, y0, nn);
+              if (nplanes == 2) tma_load_4d(map_lo, a_full(as), sA + a_plane, ck.c0, x0 + ld.dx, y0, nn);
+            }
             if (++as == na) { as = 0; aph ^= 1u; }
-            const int t0 = p.aload_tap0[l], t1 = t0 + p.aload_ntaps[l];
-            for (int t = t0; t < t1; ++t) {
-              mbar_wait(w_empty(ws), wph ^ 1u, p.err_flag, 2);
-              mbar_expect_tx(w_full(ws), nplanes * p.w_plane_bytes);
-              const uint32_t sW = w_base + ws * w_slot_bytes;
-              const int wrow = t * p.g.cout_pad + nb * p.n_tile;
-              tma_load_2d(&p.w_map[0], w_full(ws), sW, c * EGN_KC, wrow);
-              if (nplanes == 2) tma_load_2d(&p.w_map[1], w_full(ws), sW + p.w_plane_bytes, c * EGN_KC, wrow);
-              if (++ws == nw) { ws = 0; wph ^= 1u; }
+            if (p.w_box) {
+              // runs of up to w_slot_taps taps share one weight slot / barrier round trip
+              for (int t0 = 0; t0 < ld.ntaps; t0 += p.w_slot_taps) {
+                const int nrun = min(p.w_slot_taps, ld.ntaps - t0);
+                if (ptm) ptm_c0 = clock64();
+                mbar_wait(w_empty(ws), wph ^ 1u, p.err_flag, 2);
+                if (ptm) ptm_w += clock64() - ptm_c0;
+                const uint32_t sW = w_base + ws * w_slot_bytes;
+                if (dbg & 8) {
+                  mbar_arrive(w_full(ws));
+                } else {
+                  mbar_expect_tx(w_full(ws), w_tx * nrun);
+                  for (int j = 0; j < nrun; ++j) {
+                    const int wrow = (ld.tap0 + t0 + j) * cout_pad + wrow0;
+                    tma_load_2d(&p.w_map[0], w_full(ws), sW + j * w_tap_bytes, c * EGN_KC, wrow);
+                    if (nplanes == 2) tma_load_2d(&p.w_map[1], w_full(ws), sW + j * w_tap_bytes + w_plane, c * EGN_KC, wrow);
+                  }
+                }
+                if (++ws == nw) { ws = 0; wph ^= 1u; }
+              }
+            } else {
+              for (int t = ld.tap0; t < ld.tap0 + ld.ntaps; ++t) {
+                if (ptm) ptm_c0 = clock64();
+                mbar_wait(w_empty(ws), wph ^ 1u, p.err_flag, 2);
+                if (ptm) ptm_w += clock64() - ptm_c0;
+                const uint32_t sW = w_base + ws * w_slot_bytes;
+                const int wrow = t * cout_pad + wrow0;
+                if (dbg & 8) {
+                  mbar_arrive(w_full(ws));
+                } else {
+                  mbar_expect_tx(w_full(ws), w_tx);
+                  tma_load_2d(&p.w_map[0], w_full(ws), sW, c * EGN_KC, wrow);
+                  if (nplanes == 2) tma_load_2d(&p.w_map[1], w_full(ws), sW + w_plane, c * EGN_KC, wrow);
+                }
+                if (++ws == nw) { ws = 0; wph ^= 1u; }
+              }
             }
           }
         }
+      }
+      if (ptm) {
+        long long* o = p.timing + (size_t)blockIdx.x * 10;
+        o[6] = ptm_a; o[7] = ptm_w; o[8] = clock64() - ptm_start;
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    // The whole warp walks the schedule (convergent waits); one elected lane issues the MMAs.
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
-                           ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t sub_cols = (uint32_t)(p.g.groups * p.n_tile);
-    int as = 0, ws = 0;
-    uint32_t aph = 0, wph = 0;
-    int use = 0;                                   // tiles issued so far by this CTA
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++use) {
-      const int ty = (tile / (p.n_blocks * p.tiles_x)) % p.tiles_y;
-      const int nsub = min(p.S, (p.g.H - ty * p.tr + p.sr - 1) / p.sr);
-      const int ab = p.acc_bufs == 2 ? (use & 1) : 0;
-      const uint32_t aphase = (p.acc_bufs == 2 ? (use >> 1) : use) & 1u;
-      mbar_wait(tempty_bar(ab), aphase ^ 1u, p.err_flag, 3);
-      fence_after();
-      uint32_t started = 0;
-      for (int c = 0; c < p.g.nchunks; ++c) {
-        for (int l = 0; l < p.n_aloads; ++l) {
-          mbar_wait(a_full(as), aph, p.err_flag, 4);
-          const uint32_t sA = base + as * a_slot_bytes;
-          const int t0 = p.aload_tap0[l], t1 = t0 + p.aload_ntaps[l];
-          for (int t = t0; t < t1; ++t) {
-            mbar_wait(w_full(ws), wph, p.err_flag, 5);
-            fence_after();
-            const uint32_t sW = w_base + ws * w_slot_bytes;
-            const int grp = p.g.tap_grp[t];
-            const uint32_t a_off = (uint32_t)((p.g.tap_dy[t] + p.dmax) << p.bw_log2) * 64u;
-            const uint32_t first = ((started >> grp) & 1u) ^ 1u;
-            const uint32_t d_tmem = tmem_base + ab * TC_ACC_STRIDE + grp * p.n_tile;
-            if (elect_one()) {
-              if (p.dbg & 2) {
-              } else if (nplanes == 2) {
-                if (nsub == 4) issue_tap<4, 2>(sA + a_off, p.a_plane_bytes, sW, p.w_plane_bytes, d_tmem, sub_cols, idesc, first);
-                else if (nsub == 2) issue_tap<2, 2>(sA + a_off, p.a_plane_bytes, sW, p.w_plane_bytes, d_tmem, sub_cols, idesc, first);
-                else if (nsub == 3) issue_tap<3, 2>(sA + a_off, p.a_plane_bytes, sW, p.w_plane_bytes, d_tmem, sub_cols, idesc, first);
-                else issue_tap<1, 2>(sA + a_off, p.a_plane_bytes, sW, p.w_plane_bytes, d_tmem, sub_cols, idesc, first);
-              } else {
-                if (nsub == 4) issue_tap<4, 1>(sA + a_off, 0, sW, 0, d_tmem, sub_cols, idesc, first);
-                else if (nsub == 2) issue_tap<2, 1>(sA + a_off, 0, sW, 0, d_tmem, sub_cols, idesc, first);
-                else if (nsub == 3) issue_tap<3, 1>(sA + a_off, 0, sW, 0, d_tmem, sub_cols, idesc, first);
-                else issue_tap<1, 1>(sA + a_off, 0, sW, 0, d_tmem, sub_cols, idesc, first);
+    // The whole warp walks the schedule with warp-uniform control flow (so addresses and
+    // descriptors live in uniform registers and the MMAs issue back to back); per tap it reads one
+    // shared-memory entry, waits on the operand barriers (usually already complete) and one
+    // elected lane issues NSUB x 2 x (1 or 3) MMAs plus the commits that free the slots.
+    {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) |
+                             ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc_wide = (1u << 4) | (1u << 7) | (1u << 10) |
+                                  ((uint32_t)((2 * p.n_tile) >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t sub_cols = (uint32_t)(p.g.groups * p.n_tile * (p.wide_b ? 2 : 1));
+      const int nchunks = p.g.nchunks, ntaps = p.g.ntaps;
+      const uint32_t a_plane = p.a_plane_bytes, w_plane = p.w_plane_bytes;
+      const int dbg = p.dbg;
+      int as = 0, ws = 0;
+      uint32_t aph = 0, wph = 0;
+      int use = 0;                                   // tiles issued so far by this CTA
+      const bool tm = p.timing != nullptr;
+      long long tm_te = 0, tm_a = 0, tm_w = 0, tm_i = 0, tm_k = 0, tm_c0 = 0;
+      const long long tm_start = tm ? clock64() : 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++use) {
+        const int ty = (tile / (p.n_blocks * p.tiles_x)) % p.tiles_y;
+        const int nsub = min(p.S, (p.g.H - ty * p.tr + p.sr - 1) / p.sr);
+        const int ab = p.acc_bufs == 2 ? (use & 1) : 0;
+        const uint32_t aphase = (p.acc_bufs == 2 ? (use >> 1) : use) & 1u;
+        if (tm) tm_c0 = clock64();
+        mbar_wait(tempty_bar(ab), aphase ^ 1u, p.err_flag, 3);
+        if (tm) tm_te += clock64() - tm_c0;
+        fence_after();
+        const uint32_t d_base = tmem_base + ab * TC_ACC_STRIDE;
+        auto run_tile = [&](auto nsub_c, auto npl_c, auto wide_c) {
+          constexpr int NSUB = decltype(nsub_c)::value;
+          constexpr int NPL = decltype(npl_c)::value;
+          constexpr int WIDE = decltype(wide_c)::value;
+          if (p.w_box) {
+            // one weight-barrier round trip per run of up to three taps instead of one per tap
+            const int n_aloads = p.n_aloads;
+            for (int c = 0; c < nchunks; ++c) {
+              for (int l = 0; l < n_aloads; ++l) {
+                const TcLoad ld = s_load[l];
+                if (tm) tm_c0 = clock64();
+                mbar_wait(a_full(as), aph, p.err_flag, 4);
+                if (tm) tm_a += clock64() - tm_c0;
+                const uint32_t sA = base + as * a_slot_bytes;
+                for (int t0 = 0; t0 < ld.ntaps; t0 += p.w_slot_taps) {
+                  const int nrun = min(p.w_slot_taps, ld.ntaps - t0);
+                  const bool last_run = t0 + nrun >= ld.ntaps;
+                  if (tm) tm_c0 = clock64();
+                  mbar_wait(w_full(ws), wph, p.err_flag, 5);
+                  if (tm) { const long long now = clock64(); tm_w += now - tm_c0; tm_c0 = now; }
+                  fence_after();
+                  const uint32_t sW = w_base + ws * w_slot_bytes;
+                  if (elect_one()) {
+                    if (!(dbg & 2)) {
+                      TcTapStep nxt = s_tap[ld.tap0 + t0];
+                      for (int j = 0; j < nrun; ++j) {
+                        const TcTapStep cur = nxt;
+                        if (j + 1 < nrun) nxt = s_tap[ld.tap0 + t0 + j + 1];
+                        const uint32_t first = (c == 0 && (cur.flags & 4u)) ? 1u : 0u;
+                        issue_tap<NSUB, NPL, WIDE>(sA + cur.a_off, a_plane, sW + j * w_tap_bytes, w_plane, d_base + cur.d_col, sub_cols, idesc, idesc_wide, first);
+                      }
+                    }
+                    if (tm) { const long long now = clock64(); tm_i += now - tm_c0; tm_c0 = now; }
+                    mma_commit(w_empty(ws));
+                    if (last_run) mma_commit(a_empty(as));
+                    if (tm) tm_k += clock64() - tm_c0;
+                  }
+                  __syncwarp();
+                  if (++ws == nw) { ws = 0; wph ^= 1u; }
+                }
+                if (++as == na) { as = 0; aph ^= 1u; }
               }
-              mma_commit(w_empty(ws));             // frees the weight slot when these MMAs retire
-              if (t + 1 == t1) mma_commit(a_empty(as));   // last tap of this box
             }
-            __syncwarp();
-            started |= 1u << grp;
-            if (++ws == nw) { ws = 0; wph ^= 1u; }
+            return;
           }
-          if (++as == na) { as = 0; aph ^= 1u; }
+          for (int c = 0; c < nchunks; ++c) {
+            uint32_t sA = 0;
+            TcTapStep nxt = s_tap[0];
+            for (int t = 0; t < ntaps; ++t) {
+              const TcTapStep cur = nxt;
+              if (t + 1 < ntaps) nxt = s_tap[t + 1];
+              if (cur.flags & 1u) {
+                if (tm) tm_c0 = clock64();
+                mbar_wait(a_full(as), aph, p.err_flag, 4);
+                if (tm) tm_a += clock64() - tm_c0;
+                sA = base + as * a_slot_bytes;
+              }
+              if (tm) tm_c0 = clock64();
+              mbar_wait(w_full(ws), wph, p.err_flag, 5);
+              if (tm) { const long long now = clock64(); tm_w += now - tm_c0; tm_c0 = now; }
+              fence_after();
+              const uint32_t sW = w_base + ws * w_slot_bytes;
+              const uint32_t first = (c == 0 && (cur.flags & 4u)) ? 1u : 0u;
+              if (elect_one()) {
+                if (!(dbg & 2))
+                  issue_tap<NSUB, NPL, WIDE>(sA + cur.a_off, a_plane, sW, w_plane, d_base + cur.d_col, sub_cols, idesc, idesc_wide, first);
+                if (tm) { const long long now = clock64(); tm_i += now - tm_c0; tm_c0 = now; }
+                mma_commit(w_empty(ws));             // frees the weight slot when these MMAs retire
+                if (cur.flags & 2u) mma_commit(a_empty(as));   // last tap of this box
+                if (tm) tm_k += clock64() - tm_c0;
+              }
+              __syncwarp();
+              if (++ws == nw) { ws = 0; wph ^= 1u; }
+              if (cur.flags & 2u) {
+                if (++as == na) { as = 0; aph ^= 1u; }
+              }
+            }
+          }
+        };
+        using std::integral_constant;
+        typedef integral_constant<int, 0> I0;
+        typedef integral_constant<int, 1> I1;
+        typedef integral_constant<int, 2> I2;
+        typedef integral_constant<int, 3> I3;
+        typedef integral_constant<int, 4> I4;
+        if (nplanes == 2 && p.wide_b) {
+          if (nsub == 4) run_tile(I4{}, I2{}, I1{});
+          else if (nsub == 2) run_tile(I2{}, I2{}, I1{});
+          else if (nsub == 3) run_tile(I3{}, I2{}, I1{});
+          else run_tile(I1{}, I2{}, I1{});
+        } else if (nplanes == 2) {
+          if (nsub == 4) run_tile(I4{}, I2{}, I0{});
+          else if (nsub == 2) run_tile(I2{}, I2{}, I0{});
+          else if (nsub == 3) run_tile(I3{}, I2{}, I0{});
+          else run_tile(I1{}, I2{}, I0{});
+        } else {
+          if (nsub == 4) run_tile(I4{}, I1{}, I0{});
+          else if (nsub == 2) run_tile(I2{}, I1{}, I0{});
+          else if (nsub == 3) run_tile(I3{}, I1{}, I0{});
+          else run_tile(I1{}, I1{}, I0{});
         }
+        if (elect_one()) mma_commit(tfull_bar(ab));  // accumulators complete -> epilogue
+        __syncwarp();
       }
-      if (elect_one()) mma_commit(tfull_bar(ab));  // accumulators complete -> epilogue
-      __syncwarp();
+      if (tm) {
+        // counters are summed over lanes by the elected thread only for tm_i / tm_k
+        long long* o = p.timing + (size_t)blockIdx.x * 10;
+        if (lane == 0) { o[0] = clock64() - tm_start; o[1] = tm_te; o[2] = tm_a; o[3] = tm_w; o[5] = use; }
+        if (tm_i) { o[4] = tm_i; o[9] = tm_k; }
+      }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9)
@@ -463,8 +641,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           for (int i = 0; i < 32; ++i) sacc[i] = 0.f;
           for (int s0 = 0; s0 < nsub; s0 += 2) {
             uint32_t r[2][16];
-            tmem_ld16(tbase + s0 * p.n_tile + c0, r[0]);
-            if (s0 + 1 < nsub) tmem_ld16(tbase + (s0 + 1) * p.n_tile + c0, r[1]);
+            const uint32_t sstride = p.wide_b ? 2 * p.n_tile : p.n_tile;
+            tmem_ld16(tbase + s0 * sstride + c0, r[0]);
+            if (s0 + 1 < nsub) tmem_ld16(tbase + (s0 + 1) * sstride + c0, r[1]);
+            if (p.wide_b) {                        // add the hi*lo partial sums held in columns [n, 2n)
+              uint32_t q[2][16];
+              tmem_ld16(tbase + s0 * sstride + p.n_tile + c0, q[0]);
+              if (s0 + 1 < nsub) tmem_ld16(tbase + (s0 + 1) * sstride + p.n_tile + c0, q[1]);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                r[0][i] = __float_as_uint(__uint_as_float(r[0][i]) + __uint_as_float(q[0][i]));
+                r[1][i] = __float_as_uint(__uint_as_float(r[1][i]) + __uint_as_float(q[1][i]));
+              }
+            }
             tmem_ld_wait();
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -610,8 +800,8 @@ static void make_w_map(CUtensorMap* map, const bf16* ptr, int rows, int kpad, in
 
 static size_t tc_smem_bytes(const TcParams& p) {
   const int nplanes = p.nsplit == 1 ? 1 : 2;
-  return 1024 + (size_t)p.na * nplanes * p.a_plane_bytes + (size_t)p.nw * nplanes * p.w_plane_bytes +
-         8 * (2 * p.na + 2 * p.nw + 4) + 16 + (2 * 2 * 4 * 32 + 768 + 512 + 512) * sizeof(float);
+  return 1024 + (size_t)p.na * nplanes * p.a_plane_bytes + (size_t)p.nw * p.w_slot_taps * nplanes * p.w_plane_bytes +
+         8 * (2 * p.na + 2 * p.nw + 4) + 16 + (2 * 2 * 4 * 32 + 768 + 512 + 512) * sizeof(float) + TC_SCHED_BYTES;
 }
 
 // Fills the tiling fields of `p` from the geometry (taps must be sorted by dx) and sizes the rings.
@@ -619,6 +809,9 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   const ConvGeom& g = p.g;
   p.nsplit = nsplit;
   p.n_blocks = ceil_div(cout_pad, 256);
+  // wide layers run as 256-pixel x 128-channel CTA tiles (two sub-tiles, both TMEM buffers): the
+  // weight stream per tile halves against 128 x 256 and a run of three taps fits one weight slot
+  if (cout_pad >= 256 && cout_pad % 128 == 0 && !getenv("EGN_TC_N256")) p.n_blocks = cout_pad / 128;
   EGN_CHECK(cout_pad % (16 * p.n_blocks) == 0, "cout_pad must split into equal 16-aligned N tiles");
   p.n_tile = cout_pad / p.n_blocks;
   EGN_CHECK(p.n_tile % 16 == 0 && p.n_tile <= 256, "bad n_tile");
@@ -627,7 +820,11 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   const int bw = padded(8) < padded(16) ? 8 : 16;
   p.bw_log2 = bw == 8 ? 3 : 4;
   p.sr = 128 / bw;
-  const int cols = g.groups * p.n_tile;
+  // narrow single-group layers are bound by the shared-memory read of the activation tile (an
+  // M=128, N<=64 MMA takes (128+N)/4 cycles, tools/mma_probe.cu): fold hi*hi and hi*lo into one MMA
+  p.wide_b = (nsplit == 3 && g.groups == 1 && p.n_tile <= 64) ? 1 : 0;
+  if (const char* e = getenv("EGN_TC_WIDE")) p.wide_b = atoi(e) ? p.wide_b : 0;
+  const int cols = g.groups * p.n_tile * (p.wide_b ? 2 : 1);
   EGN_CHECK(cols <= 512, "accumulator groups exceed TMEM");
   // more sub-tiles per CTA tile amortise the weight stream and give the MMA pipe independent
   // accumulators to interleave; prefer shapes that keep two TMEM buffers
@@ -667,12 +864,22 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   p.a_plane_bytes = (p.a_box_bytes + 1023u) & ~1023u;
   p.w_plane_bytes = (uint32_t)p.n_tile * 64u;
   const int nplanes = nsplit == 1 ? 1 : 2;
-  const size_t budget = 227 * 1024 - 1024 - 512 - 2048 - 7168;
+  const size_t budget = 227 * 1024 - 1024 - 512 - 2048 - 7168 - TC_SCHED_BYTES;
   const size_t a_slot = (size_t)nplanes * p.a_plane_bytes, w_slot = (size_t)nplanes * p.w_plane_bytes;
+  // small N: an MMA is short (40-48 cycles) and the issue queue holds only ~8 of them, so the
+  // per-tap barrier round trips of the weight ring would starve the pipe; load every tap of a box
+  // into one slot instead (measured with tools/mma_queue_probe.cu)
+  int max_box_taps = 1;
+  for (int l = 0; l < p.n_aloads; ++l) max_box_taps = std::max(max_box_taps, (int)p.aload_ntaps[l]);
+  p.w_box = 1;
+  if (const char* e = getenv("EGN_TC_WBOX")) p.w_box = atoi(e) ? p.w_box : 0;
+  p.w_slot_taps = p.w_box ? std::min(max_box_taps, 3) : 1;
+  if (budget < 2 * a_slot + 2 * w_slot * p.w_slot_taps) { p.w_box = 0; p.w_slot_taps = 1; }   // 256-wide tiles: one tap per slot
+  const size_t w_slot_all = w_slot * p.w_slot_taps;
   p.na = 2;
-  EGN_CHECK(budget > p.na * a_slot + 2 * w_slot, "conv_tc: tile does not fit in shared memory");
-  p.nw = (int)std::min<size_t>(8, (budget - p.na * a_slot) / w_slot);
-  while (p.na < 4 && budget >= (p.na + 1) * a_slot + (size_t)p.nw * w_slot) ++p.na;
+  EGN_CHECK(budget > p.na * a_slot + 2 * w_slot_all, "conv_tc: tile does not fit in shared memory");
+  p.nw = (int)std::min<size_t>(p.w_box ? 3 : 8, (budget - p.na * a_slot) / w_slot_all);
+  while (p.na < 4 && budget >= (p.na + 1) * a_slot + (size_t)p.nw * w_slot_all) ++p.na;
 }
 
 static void tc_launch(const TcParams& p, int num_sms, cudaStream_t stream) {
@@ -685,6 +892,25 @@ static void tc_launch(const TcParams& p, int num_sms, cudaStream_t stream) {
   const size_t smem = tc_smem_bytes(p);
   EGN_CHECK(smem <= 227 * 1024, "conv_tc smem budget exceeded");
   int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  static const bool timing = getenv("EGN_TC_TIMING") != nullptr;
+  if (timing) {
+    // debugging aid: per-role cycle counters of one launch, averaged over CTAs, to stderr
+    static long long* buf = nullptr;
+    if (!buf) CUDA_OK(cudaMalloc(&buf, 148 * 10 * sizeof(long long)));
+    CUDA_OK(cudaMemsetAsync(buf, 0, 148 * 10 * sizeof(long long), stream));
+    TcParams q = p;
+    q.timing = buf;
+    conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(q);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(stream));
+    long long h[148 * 10];
+    CUDA_OK(cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost));
+    double a[10] = {0};
+    for (int b = 0; b < grid; ++b) for (int k = 0; k < 10; ++k) a[k] += (double)h[b * 10 + k] / grid;
+    fprintf(stderr, "tc_timing H=%d W=%d chunks=%d taps=%d ntile=%d S=%d na=%d nw=%d batch=%d | mma: total %.0f tempty %.0f a_full %.0f w_full %.0f issue %.0f commit %.0f tiles %.1f | prod: a_empty %.0f w_empty %.0f total %.0f\n",
+            p.g.H, p.g.W, p.g.nchunks, p.g.ntaps, p.n_tile, p.S, p.na, p.nw, p.g.batch, a[0], a[1], a[2], a[3], a[4], a[9], a[5], a[6], a[7], a[8]);
+    return;
+  }
   conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
   CUDA_OK(cudaGetLastError());
 }

@@ -327,7 +327,7 @@ struct Engine {
     L.simt.w_hi = L.w_hi; L.simt.w_lo = L.w_lo;
     for (int s = 0; s < EGN_MAX_SRC; ++s) L.simt.src[s] = L.src[s];
     // tensor-core parameters
-    L.tc.g = L.g; L.tc.e = L.e; L.tc.err_flag = err_flag;
+    L.tc.g = L.g; L.tc.e = L.e; L.tc.err_flag = err_flag; L.tc.timing = nullptr;
     if (use_tc) {
       tc_configure(L.tc, L.g.cout_pad, nsplit);
       for (int s = 0; s < L.nsrc; ++s) {
