@@ -49,7 +49,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append([c.strip() for c in out.strip().split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
@@ -84,6 +84,25 @@ def cpu_reference_fps(frames, repeats, threads):
     return frames / best, best
 
 
+def workload_config(config, batch, world, micro_batch):
+    return {"workload": "%s.yaml: BDCN edge extractor + ESF-Net, batch %d per GPU, 240x320" % (config, batch),
+            "global_batch": batch * world, "micro_batch": micro_batch,
+            "parallelism": "dp%d (batch-sharded frames)" % world,
+            "cache": "working set per step (%.1f GB activations) exceeds the 126 MB L2; no flush needed" % (micro_batch * 0.4),
+            "weights": "synthetic seeded checkpoints in the reference container formats"}
+
+
+def conv_traffic():
+    """Per-launch DRAM traffic of conv_tc_kernel from the committed ncu capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    if os.path.isfile(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
 def run_reference(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -112,8 +131,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "baseline_edge.yaml: BDCN edge extractor + ESF-Net, 240x320 frames",
-                       "sample": "%d frames per step on the host CPU" % frames},
+            "config": dict(workload_config(args.config, args.batch, max(1, args.gpus), args.micro_batch),
+                           sample="%d frames per step on the host CPU (bounded sample of the %d-frame batch)" % (frames, args.batch)),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                              "sample": "%d steps x %d frames, oracle/graph.py (torch fp32), all host threads" % (args.steps, frames)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -236,22 +255,23 @@ def main():
     peak_tf, peak_gbs, peak_src = read_peaks()
     achieved = conv_flops / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
     gf = GFLOP_PER_FRAME.get(args.config)
+    traffic = conv_traffic()
     if rank == 0:
         line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)", "data": "synthetic",
-                "config": {"workload": "%s.yaml: BDCN edge extractor + ESF-Net, batch %d per GPU, 240x320" % (args.config, B),
-                           "global_batch": B * world, "micro_batch": args.micro_batch, "parallelism": "dp%d (batch-sharded frames)" % world,
-                           "cache": "working set per step (%.1f GB activations) exceeds the 126 MB L2; no flush needed" %
-                                    (args.micro_batch * 0.4),
-                           "weights": "synthetic seeded checkpoints in the reference container formats"},
+                "config": workload_config(args.config, B, world, args.micro_batch),
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
                         "d2h_bytes_per_step": int(out_am.numel() + 4 * (out_el.numel() + out_eo.numel() + out_lat.numel())),
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (all %d conv launches of the timed region)" % conv_n,
                              "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                             "peak_source": peak_src, "traffic": None,
+                             "peak_source": peak_src,
+                             "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                             "traffic_note": (traffic or {}).get("note", "no ncu capture committed yet"),
+                             "algorithmic_flops_per_launch": conv_flops / conv_n if conv_n else None,
+                             "ms_per_launch": conv_ms / conv_n if conv_n else None,
                              "kernel_share_of_step": conv_ms / ms if ms > 0 else None,
                              "whole_step_tflops": fps / world * gf / 1000.0 if gf else None,
                              "whole_step_frac": fps / world * gf / 1000.0 / peak_tf if gf else None},

@@ -31,113 +31,151 @@ struct FirstConvParams {
   int B, H, W, cout, act;
 };
 
+#define FC_TW 32   // tile width (pixels)
+#define FC_TH 8    // tile height
+
+// Block = 8 x 32 output pixels.  The fp32 input window (10 x 34 per plane) and the weights are
+// staged in shared memory; a thread produces 8 output channels of 4 horizontally adjacent pixels,
+// so each weight read serves four pixels and each input value is read once per 8 channels.
+template <int CIN, int COUT>
 __global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p) {
-  // weights [cin][9][cout] staged in shared memory and read as float4 (broadcast within a pixel);
-  // each thread produces 8 output channels of two horizontally adjacent pixels
-  extern __shared__ float fc_sw[];
-  const int wn = p.cin * 9 * p.cout;
-  for (int i = threadIdx.x; i < wn; i += blockDim.x) fc_sw[i] = p.w[i];
-  __syncthreads();
-  const int groups = p.cout / 8;
-  const int Wh = p.W / 2;
-  const long long total = (long long)p.B * p.H * Wh * groups;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int gidx = (int)(idx % groups);
-  const long long pp = idx / groups;
-  const int x = (int)(pp % Wh) * 2;
-  const int y = (int)((pp / Wh) % p.H);
-  const int n = (int)(pp / ((long long)Wh * p.H));
-  float acc0[8], acc1[8];
+  constexpr int G = COUT / 8;                 // 8-channel groups
+  __shared__ __align__(16) float sw[CIN * 9 * COUT];           // [cin][tap][half][group][4]
+  __shared__ float tile[CIN][FC_TH + 2][FC_TW + 2];
+  const int n = blockIdx.z, y0 = blockIdx.y * FC_TH, x0 = blockIdx.x * FC_TW;
+  for (int i = threadIdx.x; i < CIN * 9 * COUT; i += 256) {
+    const int co = i % COUT, ct = i / COUT;                    // p.w is [cin][tap][cout]
+    const int g = co >> 3, h = (co >> 2) & 1, k = co & 3;
+    sw[((ct * 2 + h) * G + g) * 4 + k] = p.w[i];
+  }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc0[i] = acc1[i] = __ldg(p.bias + gidx * 8 + i);
-  for (int ci = 0; ci < p.cin; ++ci) {
+  for (int ci = 0; ci < CIN; ++ci) {
     const float* in = p.in[ci] + (size_t)n * p.fstride[ci];
+    for (int i = threadIdx.x; i < (FC_TH + 2) * (FC_TW + 2); i += 256) {
+      const int ty = i / (FC_TW + 2), tx = i % (FC_TW + 2);
+      const int yy = y0 + ty - 1, xx = x0 + tx - 1;
+      tile[ci][ty][tx] = (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) ? __ldg(in + (size_t)yy * p.W + xx) : 0.f;
+    }
+  }
+  __syncthreads();
+  constexpr int RUNS = FC_TH * FC_TW / 4;      // runs of 4 pixels in the tile
+  for (int item = threadIdx.x; item < RUNS * G; item += 256) {
+    const int g = item % G, run = item / G;
+    const int ty = run / (FC_TW / 4), tx = (run % (FC_TW / 4)) * 4;
+    float acc[4][8];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(p.bias + g * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(p.bias + g * 8 + 4);
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int yy = y + r - 1;
-      if (yy < 0 || yy >= p.H) continue;
-      const float* row = in + (size_t)yy * p.W;
-      float a[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int xx = x + j - 1;
-        a[j] = (xx >= 0 && xx < p.W) ? __ldg(row + xx) : 0.f;
+      for (int q = 0; q < 4; ++q) {
+        acc[q][0] = b0.x; acc[q][1] = b0.y; acc[q][2] = b0.z; acc[q][3] = b0.w;
+        acc[q][4] = b1.x; acc[q][5] = b1.y; acc[q][6] = b1.z; acc[q][7] = b1.w;
       }
+    }
 #pragma unroll
-      for (int s2 = 0; s2 < 3; ++s2) {
-        const float4* w4 = reinterpret_cast<const float4*>(fc_sw + ((size_t)(ci * 9 + r * 3 + s2)) * p.cout + gidx * 8);
-        const float4 wa = w4[0], wb = w4[1];
-        const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+    for (int ci = 0; ci < CIN; ++ci) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          acc0[i] = fmaf(a[s2], w[i], acc0[i]);
-          acc1[i] = fmaf(a[s2 + 1], w[i], acc1[i]);
+      for (int r = 0; r < 3; ++r) {
+        float a[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) a[j] = tile[ci][ty + r][tx + j];
+#pragma unroll
+        for (int s2 = 0; s2 < 3; ++s2) {
+          const int ct = ci * 9 + r * 3 + s2;
+          const float4 wa = *reinterpret_cast<const float4*>(sw + ((ct * 2 + 0) * G + g) * 4);
+          const float4 wb = *reinterpret_cast<const float4*>(sw + ((ct * 2 + 1) * G + g) * 4);
+          const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[q][i] = fmaf(a[s2 + q], w[i], acc[q][i]);
+        }
+      }
+    }
+    const int y = y0 + ty, x = x0 + tx;
+    if (y < p.H) {
+      const size_t o = ((size_t)(n + p.dst.n_off) * p.H * p.W + (size_t)y * p.W + x) * p.dst.C + p.dst.coff + g * 8;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (x + q < p.W) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[q][i] = apply_act(acc[q][i], p.act);
+          store8(p.dst.hi, p.dst.lo, o + (size_t)q * p.dst.C, acc[q]);
         }
       }
     }
   }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { acc0[i] = apply_act(acc0[i], p.act); acc1[i] = apply_act(acc1[i], p.act); }
-  const size_t o = ((size_t)(n + p.dst.n_off) * p.H * p.W + (size_t)y * p.W + x) * p.dst.C + p.dst.coff + gidx * 8;
-  store8(p.dst.hi, p.dst.lo, o, acc0);
-  store8(p.dst.hi, p.dst.lo, o + p.dst.C, acc1);
 }
 
 // ------------------------------------------------------------------------------------------
 // Last layer: dec.final.conv2 32->3 3x3 + leaky-relu + eval BatchNorm -> fp32 NCHW logits
-// (utils.py:1046-1050).  One thread per pixel.
+// (utils.py:1046-1050).  A 16x16-pixel block stages its 18x18x32 input window in shared memory as
+// fp32 (one split-bf16 -> fp32 conversion per input value instead of nine); one thread per pixel.
+// The 864 weights travel in the kernel parameters and are read through the constant bank.
 struct LastConvParams {
   View src;             // 32 channels
-  const float* w;       // [9][32][3]
-  const float* bias;    // [3]
-  const float* scale;   // [3]  BN folded: y = act(conv)*scale + shift
-  const float* shift;
+  float w[9 * 32 * 3];  // [tap][cin][3]
+  float bias[3];
+  float scale[3];       // BN folded: y = act(conv)*scale + shift
+  float shift[3];
   float* out;           // [B][3][H][W]
   int B, H, W;
 };
 
-__global__ void __launch_bounds__(256) last_conv_kernel(const LastConvParams p) {
-  __shared__ float4 sw[9 * 32];           // [tap][cin] -> (w0, w1, w2, 0)
-  for (int i = threadIdx.x; i < 9 * 32; i += blockDim.x)
-    sw[i] = make_float4(p.w[i * 3], p.w[i * 3 + 1], p.w[i * 3 + 2], 0.f);
+#define LAST_TILE 16
+#define LAST_PITCH 36   // floats per staged pixel: 32 channels + 4 pad -> conflict-free 128-bit reads
+
+__global__ void __launch_bounds__(256) last_conv_kernel(const __grid_constant__ LastConvParams p) {
+  __shared__ __align__(16) float tile[(LAST_TILE + 2) * (LAST_TILE + 2) * LAST_PITCH];
+  const int n = blockIdx.z;
+  const int y0 = blockIdx.y * LAST_TILE, x0 = blockIdx.x * LAST_TILE;
+  constexpr int TW = LAST_TILE + 2;
+  for (int i = threadIdx.x; i < TW * TW * 4; i += 256) {
+    const int g = i & 3, pix = i >> 2;
+    const int ty = pix / TW, tx = pix % TW;
+    const int yy = y0 + ty - 1, xx = x0 + tx - 1;
+    float v[8];
+    if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+      load8(p.src.hi, p.src.lo, ((size_t)(n + p.src.n_off) * p.H * p.W + (size_t)yy * p.W + xx) * p.src.C + p.src.coff + g * 8, v);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    }
+    float4* d = reinterpret_cast<float4*>(tile + pix * LAST_PITCH + g * 8);
+    d[0] = make_float4(v[0], v[1], v[2], v[3]);
+    d[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
   __syncthreads();
-  const long long total = (long long)p.B * p.H * p.W;
-  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= total) return;
-  const int x = (int)(pix % p.W);
-  const int y = (int)((pix / p.W) % p.H);
-  const int n = (int)(pix / ((long long)p.W * p.H));
+  const int ty = threadIdx.x / LAST_TILE, tx = threadIdx.x % LAST_TILE;
+  const int y = y0 + ty, x = x0 + tx;
   float a0 = p.bias[0], a1 = p.bias[1], a2 = p.bias[2];
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    const int yy = y + r - 1;
-    if (yy < 0 || yy >= p.H) continue;
 #pragma unroll
     for (int s2 = 0; s2 < 3; ++s2) {
-      const int xx = x + s2 - 1;
-      if (xx < 0 || xx >= p.W) continue;
-      const size_t base = ((size_t)(n + p.src.n_off) * p.H * p.W + (size_t)yy * p.W + xx) * p.src.C + p.src.coff;
-      const float4* w = sw + (r * 3 + s2) * 32;
+      const float4* src = reinterpret_cast<const float4*>(tile + ((ty + r) * TW + tx + s2) * LAST_PITCH);
+      const float* w = p.w + (r * 3 + s2) * 96;
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        float v[8];
-        load8(p.src.hi, p.src.lo, base + c8 * 8, v);
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 v = src[c4];
+        const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 ww = w[c8 * 8 + i];
-          a0 = fmaf(v[i], ww.x, a0);
-          a1 = fmaf(v[i], ww.y, a1);
-          a2 = fmaf(v[i], ww.z, a2);
+        for (int k = 0; k < 4; ++k) {
+          const int c = c4 * 4 + k;
+          a0 = fmaf(vv[k], w[c * 3 + 0], a0);
+          a1 = fmaf(vv[k], w[c * 3 + 1], a1);
+          a2 = fmaf(vv[k], w[c * 3 + 2], a2);
         }
       }
     }
   }
-  const size_t hw = (size_t)p.H * p.W;
-  const size_t o = (size_t)n * 3 * hw + (size_t)y * p.W + x;
-  p.out[o] = apply_act(a0, ACT_LRELU) * p.scale[0] + p.shift[0];
-  p.out[o + hw] = apply_act(a1, ACT_LRELU) * p.scale[1] + p.shift[1];
-  p.out[o + 2 * hw] = apply_act(a2, ACT_LRELU) * p.scale[2] + p.shift[2];
+  if (y < p.H && x < p.W) {
+    const size_t hw = (size_t)p.H * p.W;
+    const size_t o = (size_t)n * 3 * hw + (size_t)y * p.W + x;
+    p.out[o] = apply_act(a0, ACT_LRELU) * p.scale[0] + p.shift[0];
+    p.out[o + hw] = apply_act(a1, ACT_LRELU) * p.scale[1] + p.shift[1];
+    p.out[o + 2 * hw] = apply_act(a2, ACT_LRELU) * p.scale[2] + p.shift[2];
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -299,35 +337,49 @@ struct UpsampleParams {
 };
 
 __global__ void __launch_bounds__(256) upsample2x_kernel(const UpsampleParams p) {
-  // one thread per (output pixel, 8-channel group); Cs is a multiple of 8 (padded channels are zero)
-  const int Ho = p.Hi * 2, Wo = p.Wi * 2;
+  // one thread per (INPUT pixel, 8-channel group): with scale 2 and half-pixel centres the four
+  // outputs (2i..2i+1, 2j..2j+1) are 0.75/0.25 blends of the 3x3 input neighbourhood (clamped at the
+  // borders), so 9 loads serve 4 stores; Cs is a multiple of 8 (padded channels are zero)
   const int groups = p.Cs / 8;
-  const long long total = (long long)p.B * Ho * Wo * groups;
+  const long long total = (long long)p.B * p.Hi * p.Wi * groups;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int gidx = (int)(idx % groups);
   const long long pix = idx / groups;
-  const int x = (int)(pix % Wo);
-  const int y = (int)((pix / Wo) % Ho);
-  const int n = (int)(pix / ((long long)Wo * Ho));
-  const float sy = fmaxf(0.f, (y + 0.5f) * 0.5f - 0.5f);
-  const float sx = fmaxf(0.f, (x + 0.5f) * 0.5f - 0.5f);
-  const int y0 = (int)sy, x0 = (int)sx;
-  const int y1 = min(y0 + 1, p.Hi - 1), x1 = min(x0 + 1, p.Wi - 1);
-  const float ly = sy - y0, lx = sx - x0;
+  const int j = (int)(pix % p.Wi);
+  const int i = (int)((pix / p.Wi) % p.Hi);
+  const int n = (int)(pix / ((long long)p.Wi * p.Hi));
+  const int im = max(i - 1, 0), ip = min(i + 1, p.Hi - 1);
+  const int jm = max(j - 1, 0), jp = min(j + 1, p.Wi - 1);
   const size_t fb = (size_t)(n + p.src.n_off) * p.Hi * p.Wi;
-  float a[8], b[8], c[8], d[8], v[8];
-  load8(p.src.hi, p.src.lo, (fb + (size_t)y0 * p.Wi + x0) * p.src.C + p.src.coff + gidx * 8, a);
-  load8(p.src.hi, p.src.lo, (fb + (size_t)y0 * p.Wi + x1) * p.src.C + p.src.coff + gidx * 8, b);
-  load8(p.src.hi, p.src.lo, (fb + (size_t)y1 * p.Wi + x0) * p.src.C + p.src.coff + gidx * 8, c);
-  load8(p.src.hi, p.src.lo, (fb + (size_t)y1 * p.Wi + x1) * p.src.C + p.src.coff + gidx * 8, d);
+  const size_t cb = p.src.coff + gidx * 8;
+  float t[3][3][8];
+  const int ys[3] = {im, i, ip}, xs[3] = {jm, j, jp};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float top = (1.f - lx) * a[i] + lx * b[i];
-    const float bot = (1.f - lx) * c[i] + lx * d[i];
-    v[i] = (1.f - ly) * top + ly * bot;
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) load8(p.src.hi, p.src.lo, (fb + (size_t)ys[a] * p.Wi + xs[b]) * p.src.C + cb, t[a][b]);
+  const int Ho = p.Hi * 2, Wo = p.Wi * 2;
+  // F.interpolate(align_corners=False): source coordinate (o + 0.5) / 2 - 0.5 clamped at 0 -> for
+  // o = 2i: 0.25 * in[i-1] + 0.75 * in[i] (in[0] alone at o = 0); for o = 2i+1: 0.75 * in[i] + 0.25 * in[i+1]
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+    const int ya = dy == 0 ? 0 : 1, yb = dy == 0 ? 1 : 2;          // rows blended: (ya, yb)
+    const float wya = dy == 0 ? 0.25f : 0.75f, wyb = 1.f - wya;
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int xa = dx == 0 ? 0 : 1, xb = dx == 0 ? 1 : 2;
+      const float wxa = dx == 0 ? 0.25f : 0.75f, wxb = 1.f - wxa;
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float top = wxa * t[ya][xa][k] + wxb * t[ya][xb][k];
+        const float bot = wxa * t[yb][xa][k] + wxb * t[yb][xb][k];
+        v[k] = wya * top + wyb * bot;
+      }
+      store8(p.dst.hi, p.dst.lo, ((size_t)(n + p.dst.n_off) * Ho * Wo + (size_t)(2 * i + dy) * Wo + 2 * j + dx) * p.dst.C + p.dst.coff + gidx * 8, v);
+    }
   }
-  store8(p.dst.hi, p.dst.lo, ((size_t)(n + p.dst.n_off) * Ho * Wo + (size_t)y * Wo + x) * p.dst.C + p.dst.coff + gidx * 8, v);
 }
 
 // ------------------------------------------------------------------------------------------

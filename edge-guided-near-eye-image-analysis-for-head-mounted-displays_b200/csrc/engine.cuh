@@ -793,8 +793,8 @@ struct Engine {
       std::vector<float> shift;
       std::vector<float> scale = bn_scale(sd, "dec.final.bn", 3, 3, shift);
       es.last.src = make_view(*es.fin, 0);
-      es.last.w = mem.upload(wp); es.last.bias = mem.upload(b2.data);
-      es.last.scale = mem.upload(scale); es.last.shift = mem.upload(shift);
+      for (int i = 0; i < 9 * 32 * 3; ++i) es.last.w[i] = wp[i];
+      for (int i = 0; i < 3; ++i) { es.last.bias[i] = b2.data[i]; es.last.scale[i] = scale[i]; es.last.shift[i] = shift[i]; }
       es.last.H = 240; es.last.W = 320;
     }
     // regression head (utils.py:983-1037), fp32
@@ -868,9 +868,12 @@ struct Engine {
   }
 
   void launch_first(const FirstConvParams& fp, cudaStream_t st) {
-    const long long total = (long long)fp.B * fp.H * (fp.W / 2) * (fp.cout / 8);
-    const size_t smem = (size_t)fp.cin * 9 * fp.cout * sizeof(float);
-    first_conv_kernel<<<(unsigned)((total + 255) / 256), 256, smem, st>>>(fp);
+    const dim3 grid(ceil_div(fp.W, FC_TW), ceil_div(fp.H, FC_TH), fp.B);
+    if (fp.cout == 64 && fp.cin == 1) first_conv_kernel<1, 64><<<grid, 256, 0, st>>>(fp);
+    else if (fp.cout == 64 && fp.cin == 3) first_conv_kernel<3, 64><<<grid, 256, 0, st>>>(fp);
+    else if (fp.cout == 32 && fp.cin == 1) first_conv_kernel<1, 32><<<grid, 256, 0, st>>>(fp);
+    else if (fp.cout == 32 && fp.cin == 2) first_conv_kernel<2, 32><<<grid, 256, 0, st>>>(fp);
+    else EGN_CHECK(false, "first_conv: unsupported cin/cout");
     CUDA_OK(cudaGetLastError());
     ++launches;
   }
@@ -947,14 +950,14 @@ struct Engine {
         up.B = nb; up.Hi = u.H / 2; up.Wi = u.W / 2;
         if (i == 0) {
           up.src = make_view(*es.bt, 0, 0); up.dst = make_view(*u.buf, 0); up.Cs = 160;
-          launch_1d(upsample2x_kernel, up, (long long)nb * u.H * u.W * (up.Cs / 8), st); ++launches;
+          launch_1d(upsample2x_kernel, up, (long long)nb * up.Hi * up.Wi * (up.Cs / 8), st); ++launches;
           if (cfg.add_edge) {                                 // x = cat(x, x_add)  RITnet_v2.py:286
             up.src = make_view(*es.bt, 0, eoff); up.dst = make_view(*u.buf, 160);
-            launch_1d(upsample2x_kernel, up, (long long)nb * u.H * u.W * (up.Cs / 8), st); ++launches;
+            launch_1d(upsample2x_kernel, up, (long long)nb * up.Hi * up.Wi * (up.Cs / 8), st); ++launches;
           }
         } else {
           up.src = make_view(*es.up[i - 1].out, 0); up.dst = make_view(*u.buf, 0); up.Cs = es.up[i - 1].out_pad;
-          launch_1d(upsample2x_kernel, up, (long long)nb * u.H * u.W * (up.Cs / 8), st); ++launches;
+          launch_1d(upsample2x_kernel, up, (long long)nb * up.Hi * up.Wi * (up.Cs / 8), st); ++launches;
         }
         if (profiling) profile_end(st, 0, nullptr, "esf.upsample", 0);
         run_conv(u.c11, nb, st);
@@ -965,7 +968,10 @@ struct Engine {
       run_conv(es.final1, nb, st);
       LastConvParams lp = es.last;
       lp.B = nb; lp.out = logits + (size_t)b0 * 3 * hw;
-      aux("esf.last_conv", st, [&] { launch_1d(last_conv_kernel, lp, (long long)nb * hw, st); ++launches; });
+      aux("esf.last_conv", st, [&] {
+        last_conv_kernel<<<dim3(EGN_W / LAST_TILE, EGN_H / LAST_TILE, nb), 256, 0, st>>>(lp);
+        CUDA_OK(cudaGetLastError()); ++launches;
+      });
       // ---- AdaIN parameters from the softmaxed segmentation (RITnet_v2.py:289-308)
       if (cfg.add_seg) {
         {
