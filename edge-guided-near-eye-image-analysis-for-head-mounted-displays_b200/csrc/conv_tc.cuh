@@ -833,6 +833,7 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   const int rows_avail = ceil_div(g.H, p.sr);
   if (rows_avail >= 2 && 2 * cols <= TC_ACC_STRIDE) p.S = 2;
   if (rows_avail >= 4 && 4 * cols <= TC_ACC_STRIDE) p.S = 4;
+  if (getenv("EGN_TC_S4SINGLE") && p.wide_b && rows_avail >= 4 && 4 * cols <= 512) p.S = 4;           // tuning knob: one TMEM buffer
   if (const char* e = getenv("EGN_TC_SMAX")) p.S = std::min(p.S, std::max(1, atoi(e)));   // tuning knob
   p.tr = p.S * p.sr;
   p.acc_bufs = p.S * cols <= TC_ACC_STRIDE ? 2 : 1;

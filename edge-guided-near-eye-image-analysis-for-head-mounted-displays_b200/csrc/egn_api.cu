@@ -171,6 +171,16 @@ int egn_ellipse_refine(egn_ctx* ctx, const uint8_t* argmax_u8, const float* ell_
   API_END
 }
 
+int egn_preprocess_u8(egn_ctx* ctx, const uint8_t* frames_u8, float* out, int batch, void* stream) {
+  API_BEGIN
+  EGN_CHECK(ctx && frames_u8 && out && batch > 0, "bad argument");
+  CUDA_OK(cudaSetDevice(ctx->eng.device));
+  preprocess_u8_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(frames_u8, out);
+  CUDA_OK(cudaGetLastError());
+  ctx->eng.launches += 1;
+  API_END
+}
+
 int egn_profile(egn_ctx* ctx, int enable) {
   API_BEGIN
   EGN_CHECK(ctx, "null context");

@@ -350,3 +350,54 @@ __global__ void __launch_bounds__(REFINE_THREADS) ellipse_refine_kernel(const ui
     o[0] = center[0]; o[1] = center[1]; o[2] = now[0]; o[3] = now[1]; o[4] = now[2] / 180.0 * 3.14159;
   }
 }
+
+
+// ------------------------------------------------------------------------------------------
+// Ingest: per-frame z-score of uint8 frames, (img - mean) / std with numpy's
+// population std evaluated in float64 and the result cast to float32 (evaluate.py:102-103,
+// CurriculumLib.py:139-140).  One block per frame: exact integer sum / sum of squares, then the
+// normalised fp32 frame is written with 128-bit stores.
+__global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ out) {
+  const int n = blockIdx.x;
+  const int HW = EGN_H * EGN_W;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(in + (size_t)n * HW);
+  unsigned long long s = 0, q = 0;
+  for (int i = threadIdx.x; i < HW / 4; i += 256) {
+    const uint32_t w = __ldg(src + i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned v = (w >> (8 * k)) & 0xffu;
+      s += v; q += v * v;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  __shared__ unsigned long long ss[8], sq[8];
+  __shared__ double sh_mean, sh_std;
+  if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = s; sq[threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long S = 0, Q = 0;
+    for (int w = 0; w < 8; ++w) { S += ss[w]; Q += sq[w]; }
+    const double mean = (double)S / HW;
+    // sum (x - mean)^2 = Q - S^2 / N, exact in integers up to the final division
+    const double var = ((double)Q - (double)S * (double)S / HW) / HW;
+    sh_mean = mean;
+    sh_std = sqrt(var > 0.0 ? var : 0.0);
+  }
+  __syncthreads();
+  const double mean = sh_mean, sd = sh_std;
+  float4* dst = reinterpret_cast<float4*>(out + (size_t)n * HW);
+  for (int i = threadIdx.x; i < HW / 4; i += 256) {
+    const uint32_t w = __ldg(src + i);
+    float4 o;
+    o.x = (float)(((double)(w & 0xffu) - mean) / sd);
+    o.y = (float)(((double)((w >> 8) & 0xffu) - mean) / sd);
+    o.z = (float)(((double)((w >> 16) & 0xffu) - mean) / sd);
+    o.w = (float)(((double)(w >> 24) - mean) / sd);
+    dst[i] = o;
+  }
+}

@@ -111,6 +111,14 @@ class Context:
                                                _stream(self.device)))
         return out
 
+    def preprocess_u8(self, frames_u8):
+        """frames_u8: [B,H,W] uint8 on the device -> z-scored fp32 [B,1,H,W] (evaluate.py:102-103)."""
+        assert frames_u8.dtype == torch.uint8 and frames_u8.dim() == 3 and tuple(frames_u8.shape[1:]) == (H, W)
+        f = frames_u8.to(self.device).contiguous()
+        out = torch.empty((f.shape[0], 1, H, W), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.egn_preprocess_u8(self.h, _ptr(f), _ptr(out), int(f.shape[0]), _stream(self.device)))
+        return out
+
     # -- introspection -------------------------------------------------------------------------
     def launch_count(self):
         return int(self.lib.egn_launch_count(self.h))

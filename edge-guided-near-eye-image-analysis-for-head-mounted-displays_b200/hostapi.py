@@ -47,11 +47,12 @@ def _scratch_ctx(device):
 
 def preprocess_frames_u8(frames_u8, device):
     """evaluate.py:102-103 / CurriculumLib.py:139-140: per-frame z-score of uint8 frames
-    [B,H,W] -> fp32 [B,1,H,W] on the device (population std, like numpy)."""
-    x = torch.as_tensor(frames_u8).to(device=device, dtype=torch.float32)
-    m = x.mean(dim=(1, 2), keepdim=True)
-    s = x.var(dim=(1, 2), keepdim=True, unbiased=False).sqrt()
-    return ((x - m) / s).unsqueeze(1).contiguous()
+    [B,H,W] -> fp32 [B,1,H,W] on the device (population std in float64, like numpy); only the
+    uint8 frames cross PCIe."""
+    f = torch.as_tensor(frames_u8)
+    if f.dtype != torch.uint8:
+        raise TypeError("preprocess_frames_u8 expects uint8 frames")
+    return _scratch_ctx(torch.device(device)).preprocess_u8(f.to(device))
 
 
 class MetricAccumulator:

@@ -85,6 +85,11 @@ int egn_metrics_accumulate(egn_ctx* ctx, const uint8_t* argmax_u8, const void* l
 int egn_ellipse_refine(egn_ctx* ctx, const uint8_t* argmax_u8, const float* ell_norm, double* out,
                        int refine, int batch, void* stream);
 
+/* Replaces: the per-frame z-score of evaluate.preprocess_frame (evaluate.py:102-103) and of the
+ * DataLoader (CurriculumLib.py:139-140): (img - img.mean()) / img.std() in float64, cast to fp32.
+ * frames_u8: device [B,240,320] uint8 (already 240x320 grey); out: device [B,1,240,320] fp32. */
+int egn_preprocess_u8(egn_ctx* ctx, const uint8_t* frames_u8, float* out, int batch, void* stream);
+
 /* Per-launch timing of the convolution kernel (CUDA event pairs on the launching stream).
  * egn_profile_read returns the summed kernel milliseconds, the algorithmic FLOPs (2*MAC at the
  * reference's unpadded sizes) and the number of launches since the last reset. */

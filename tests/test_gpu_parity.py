@@ -116,7 +116,7 @@ def test_esf_tensor_core_layers_match_simt(env):
     ctx = m.context(dev)
     for layer in ["enc.head.conv2", "enc.down_block1.conv21", "enc.down_block2.conv31", "enc.down_block3.conv1",
                   "enc.bottleneck.TD.conv", "dec.up_block4.conv21", "dec.up_block3.conv11", "dec.up_block1.conv22",
-                  "dec.final.conv1"]:
+                  "dec.final.conv1", "elReg.c1"]:
         d, r = ctx.conv_selfcheck(layer, 2)
         assert d <= 1e-4 * max(r, 1.0), (layer, d, r)
 
@@ -255,3 +255,39 @@ def test_evaluate_per_image_path(env):
     got_iou = g.ell_iou(seg_map == 2, [pupil[0], pupil[1], pupil[2], pupil[3], pupil[4] * 180 / 3.14159])
     want_iou = g.ell_iou(pref == 2, [want[0], want[1], want[2], want[3], want[4] * 180 / 3.14159])
     assert got_iou >= want_iou - 0.02 or not np.isfinite(want_iou)
+
+
+def test_preprocess_u8_matches_numpy_zscore(env):
+    """evaluate.py:102-103: (img - mean) / std in float64 -> float32, on every committed real frame."""
+    egn, g, dev = env["egn"], env["graph"], env["dev"]
+    fr = np.load(os.path.join(env["golden"], "frames_u8.npz"))["frames"]
+    x = egn.preprocess_frames_u8(fr, dev).cpu().numpy()
+    want = np.stack([g.preprocess_frame_u8(f) for f in fr])[:, None]
+    assert x.shape == want.shape and x.dtype == np.float32
+    np.testing.assert_allclose(x, want, rtol=0, atol=5e-7)
+    flat = np.full((1, 240, 320), 7, np.uint8); flat[0, 0, 0] = 9      # near-constant frame: tiny std, no NaN
+    y = egn.preprocess_frames_u8(flat, dev).cpu().numpy()
+    np.testing.assert_allclose(y[0, 0], g.preprocess_frame_u8(flat[0]), rtol=1e-6, atol=1e-6)
+
+
+def test_real_frames_batch_parity(env):
+    """Eight real eye crops (videos/example1.avi via tests/golden/frames_u8.npz) through the u8 ingest,
+    BDCN and ESF-Net with a ragged micro-batch; every frame must meet the argmax / centre bars."""
+    egn, g, dev = env["egn"], env["graph"], env["dev"]
+    m, st, esd = _model(env, "baseline_edge", mb=3)
+    fr = np.load(os.path.join(env["golden"], "frames_u8.npz"))["frames"][:8]
+    x = egn.preprocess_frames_u8(fr, dev)
+    em = env["egn"].BDCN(); em.load_state_dict(env["bsd"]); em = em.cuda().eval(); em.micro_batch = 3
+    with torch.no_grad():
+        e = em.edge(x)
+        lo, eo, la, am, ep = m.infer(x, e, None)
+        e_ref = g.calc_edge(env["bsd"], x.cpu())
+        ref = g.esf_forward(esd, st, x.cpu(), e_ref)
+    np.testing.assert_allclose(e.cpu().numpy(), e_ref.numpy(), atol=5e-4)
+    agree = (am.cpu().to(torch.int64) == g.get_predictions(ref["op"])).float().flatten(1).mean(1)
+    assert agree.min().item() >= 0.999, agree
+    scale = np.array([160.0, 120.0])
+    for sl in (slice(0, 2), slice(5, 7)):
+        assert np.abs((ep.cpu().numpy()[:, sl] - ref["elPred"].numpy()[:, sl]) * scale).max() < 0.25
+    par = [2, 3, 4, 7, 8, 9]
+    assert rel_err(eo.cpu().numpy()[:, par], ref["elOut"].numpy()[:, par]) < 1e-2
