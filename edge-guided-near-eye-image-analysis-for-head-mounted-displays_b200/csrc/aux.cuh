@@ -221,49 +221,9 @@ __global__ void maxpool_kernel(const PoolParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// InstanceNorm2d(affine=False, eps=1e-5, biased variance) (RITnet_v2.py:37,56).
-// Pass 1: per-(frame, channel) sum / sum of squares in double.
-struct StatsParams {
-  View src;
-  double* sums;         // [B][Cv][2], zeroed by the caller
-  int B, HW, Cv, slabs; // Cv multiple of 8
-};
-
-__global__ void instnorm_stats_kernel(const StatsParams p) {
-  extern __shared__ double sh[];          // [Cv][2]
-  const int groups = p.Cv / 8;
-  const int n = blockIdx.y;
-  const int slab = blockIdx.x;
-  for (int i = threadIdx.x; i < p.Cv * 2; i += blockDim.x) sh[i] = 0.0;
-  __syncthreads();
-  const int rows = blockDim.x / groups;                  // pixel lanes per block
-  const int gidx = threadIdx.x % groups;
-  const int row = threadIdx.x / groups;
-  const int per = (p.HW + p.slabs - 1) / p.slabs;
-  const int p0 = slab * per;
-  const int p1 = min(p.HW, p0 + per);
-  if (row < rows) {
-    float s[8], q[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
-    for (int px = p0 + row; px < p1; px += rows) {
-      float v[8];
-      load8(p.src.hi, p.src.lo, ((size_t)(n + p.src.n_off) * p.HW + px) * p.src.C + p.src.coff + gidx * 8, v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sh[(gidx * 8 + i) * 2], (double)s[i]);
-      atomicAdd(&sh[(gidx * 8 + i) * 2 + 1], (double)q[i]);
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < p.Cv * 2; i += blockDim.x)
-    atomicAdd(&p.sums[(size_t)n * p.Cv * 2 + i], sh[i]);
-}
-
-// Pass 2: y = act((x - mean) * rstd), optionally followed by AvgPool2d(2) (Transition_down,
+// InstanceNorm2d(affine=False, eps=1e-5, biased variance) (RITnet_v2.py:37,56):
+// y = act((x - mean) * rstd) with the per-(frame, channel) sum / sum of squares accumulated by the
+// producing convolutions' epilogues, optionally followed by AvgPool2d(2) (Transition_down,
 // RITnet_v2.py:40-44; the 1x1 conv that the reference applies before the pool is applied after it
 // by the caller - both are linear, so conv(pool(z)) == pool(conv(z))).
 struct NormApplyParams {
@@ -620,64 +580,87 @@ __global__ void __launch_bounds__(HEAD_TAIL_THREADS) head_tail_kernel(const Head
   }
 }
 
-// Generic fp32 NHWC convolution (valid or zero padding, stride s) for the small head layers
-// (utils.py:992-1005) and the AdaIN style encoder (RITnet_v2.py:95-102).  Thread per (pixel, cout).
-struct ConvF32Params {
-  const float* in;    // [B][Hi][Wi][Ci]
-  const float* w;     // [kh][kw][Ci][Co]
-  const float* bias;  // [Co] or null
-  float* out;         // [B][Ho][Wo][Co]
-  int B, Hi, Wi, Ci, Ho, Wo, Co, kh, kw, stride, pad, act, reflect;
+// ------------------------------------------------------------------------------------------
+// AdaIN style encoder staging (RITnet_v2.py:91-106, Conv2dBlock utils.py:1093-1149, reflect padding).
+// Layer 0 (7x7, 3 -> 64, reflect 3): the 7 horizontal neighbours x 3 classes of the softmaxed
+// segmentation are folded into 21 (padded to 32) channels of a [B][H+6][W][32] tensor whose rows
+// already carry the vertical reflection, so the layer runs as a 7x1 convolution on the tensor cores.
+struct StyleFoldParams {
+  const float* sm;    // softmax, fp32 NHWC [B][H*W][3]
+  View dst;           // [B][H+6][W][32]
+  int B, H, W;
 };
 
-__global__ void conv_f32_kernel(const ConvF32Params p) {
-  const long long total = (long long)p.B * p.Ho * p.Wo * p.Co;
+__device__ __forceinline__ int reflect_idx(int v, int n) {
+  if (v < 0) v = -v;
+  if (v >= n) v = 2 * n - 2 - v;
+  return v;
+}
+
+__global__ void __launch_bounds__(256) style_fold_kernel(const StyleFoldParams p) {
+  const int Hp = p.H + 6;
+  const long long total = (long long)p.B * Hp * p.W * 4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int co = (int)(idx % p.Co);
-  const long long pix = idx / p.Co;
-  const int x = (int)(pix % p.Wo);
-  const int y = (int)((pix / p.Wo) % p.Ho);
-  const int n = (int)(pix / ((long long)p.Wo * p.Ho));
-  float acc = p.bias ? p.bias[co] : 0.f;
-  for (int r = 0; r < p.kh; ++r) {
-    int yy = y * p.stride + r - p.pad;
-    if (p.reflect) { if (yy < 0) yy = -yy; if (yy >= p.Hi) yy = 2 * p.Hi - 2 - yy; }
-    if (yy < 0 || yy >= p.Hi) continue;
-    for (int s = 0; s < p.kw; ++s) {
-      int xx = x * p.stride + s - p.pad;
-      if (p.reflect) { if (xx < 0) xx = -xx; if (xx >= p.Wi) xx = 2 * p.Wi - 2 - xx; }
-      if (xx < 0 || xx >= p.Wi) continue;
-      const float* a = p.in + (((size_t)n * p.Hi + yy) * p.Wi + xx) * p.Ci;
-      const float* w = p.w + ((size_t)(r * p.kw + s) * p.Ci) * p.Co + co;
-      for (int ci = 0; ci < p.Ci; ++ci) acc = fmaf(a[ci], w[(size_t)ci * p.Co], acc);
+  const int g = (int)(idx & 3);
+  const long long pix = idx >> 2;
+  const int x = (int)(pix % p.W);
+  const int r = (int)((pix / p.W) % Hp);
+  const int n = (int)(pix / ((long long)p.W * Hp));
+  const int y = reflect_idx(r - 3, p.H);
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ch = g * 8 + k;
+    float val = 0.f;
+    if (ch < 21) {
+      const int dx = ch / 3, c = ch % 3;
+      val = p.sm[((size_t)n * p.H * p.W + (size_t)y * p.W + reflect_idx(x + dx - 3, p.W)) * 3 + c];
     }
+    v[k] = val;
   }
-  p.out[idx] = apply_act(acc, p.act);
+  store8(p.dst.hi, p.dst.lo, ((size_t)(n + p.dst.n_off) * Hp * p.W + (size_t)r * p.W + x) * p.dst.C + p.dst.coff + g * 8, v);
 }
 
-// AvgPool2d(2) on fp32 NHWC (utils.py:990).
-__global__ void avgpool_f32_kernel(const float* in, float* out, int B, int Hi, int Wi, int C) {
-  const int Ho = Hi / 2, Wo = Wi / 2;
-  const long long total = (long long)B * Ho * Wo * C;
+// Layers 1-4 (4x4, stride 2, reflect 1): reflect-pad by one pixel and space-to-depth by 2, so the
+// layer becomes a 2x2 stride-1 convolution over 4C channels on the [(H+2)/2][(W+2)/2] grid (its last
+// row / column of outputs is never read).  Copies the hi/lo planes verbatim.
+struct S2dParams {
+  View src, dst;
+  int B, Hg, Wg;      // source grid (rows/cols allocated)
+  int Hs, Ws, C;      // valid source region and channels
+};
+
+__global__ void __launch_bounds__(256) s2d_reflect_kernel(const S2dParams p) {
+  const int Ho = (p.Hs + 2) / 2, Wo = (p.Ws + 2) / 2, groups = p.C / 8;
+  const long long total = (long long)p.B * Ho * Wo * 4 * groups;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int c = (int)(idx % C);
-  const long long pix = idx / C;
-  const int x = (int)(pix % Wo);
-  const int y = (int)((pix / Wo) % Ho);
-  const int n = (int)(pix / ((long long)Wo * Ho));
-  const float* b = in + (((size_t)n * Hi + 2 * y) * Wi + 2 * x) * C + c;
-  out[idx] = 0.25f * (b[0] + b[C] + b[(size_t)Wi * C] + b[(size_t)Wi * C + C]);
+  const int g = (int)(idx % groups);
+  long long rest = idx / groups;
+  const int par = (int)(rest & 3);
+  rest >>= 2;
+  const int ox = (int)(rest % Wo);
+  const int oy = (int)((rest / Wo) % Ho);
+  const int n = (int)(rest / ((long long)Wo * Ho));
+  const int sy = reflect_idx(2 * oy + (par >> 1) - 1, p.Hs), sx = reflect_idx(2 * ox + (par & 1) - 1, p.Ws);
+  const size_t si = ((size_t)(n + p.src.n_off) * p.Hg * p.Wg + (size_t)sy * p.Wg + sx) * p.src.C + p.src.coff + g * 8;
+  const size_t di = ((size_t)(n + p.dst.n_off) * Ho * Wo + (size_t)oy * Wo + ox) * p.dst.C + p.dst.coff + par * p.C + g * 8;
+  *reinterpret_cast<BF8*>(p.dst.hi + di) = *reinterpret_cast<const BF8*>(p.src.hi + si);
+  *reinterpret_cast<BF8*>(p.dst.lo + di) = *reinterpret_cast<const BF8*>(p.src.lo + si);
 }
 
-// Global average pool fp32 NHWC -> [B][C]
-__global__ void gap_f32_kernel(const float* in, float* out, int HW, int C) {
+// AdaptiveAvgPool2d(1) over the valid Hv x Wv region of a split-bf16 grid -> fp32 [B][C]
+__global__ void gap_act_kernel(View src, float* out, int Hg, int Wg, int Hv, int Wv, int C) {
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
-    for (int px = 0; px < HW; ++px) s += in[((size_t)n * HW + px) * C + c];
-    out[(size_t)n * C + c] = s / HW;
+    for (int y = 0; y < Hv; ++y)
+      for (int x = 0; x < Wv; ++x) {
+        const size_t i = ((size_t)(n + src.n_off) * Hg * Wg + (size_t)y * Wg + x) * src.C + src.coff + c;
+        s += join_bf16(src.hi[i], src.lo[i]);
+      }
+    out[(size_t)n * C + c] = s / (float)(Hv * Wv);
   }
 }
 

@@ -176,8 +176,11 @@ struct Engine {
     Act *hin, *c1o;               // AdaIN-transformed head input (add_seg only); lrelu(c1(x))
     ConvLayer head_c1;
     HeadTailParams head;
-    float *sm, *se[5], *gap, *sty, *m1, *m2, *adain;
-    float *w_se[5], *b_se[5], *w_se6, *b_se6, *w_m[3], *b_m[3];
+    float *sm, *gap, *sty, *m1, *m2, *adain;
+    Act *st_in[5], *st_out[5];    // style encoder: staged (folded / space-to-depth) inputs and outputs
+    ConvLayer st_conv[5];
+    std::vector<float> st_w[5];   // host copies of the remapped style-encoder weights (build time only)
+    float *w_se6, *b_se6, *w_m[3], *b_m[3];
     float* logits_tmp;
     double* stats_all;
     size_t stats_bytes;
@@ -841,14 +844,47 @@ struct Engine {
     }
     es.adain = nullptr;
     if (cfg.add_seg) {
-      // StyleEncoder + MLP (RITnet_v2.py:91-121), fp32 NHWC
-      const int sh[5] = {240, 120, 60, 30, 15}, sw_[5] = {320, 160, 80, 40, 20}, sc[5] = {64, 128, 256, 256, 256};
+      // StyleEncoder (RITnet_v2.py:91-106) on the tensor cores: layer 0 as a 7x1 convolution over the
+      // horizontally folded softmax (aux.cuh style_fold_kernel), layers 1-4 as 2x2 convolutions over the
+      // reflect-padded space-to-depth of their input (s2d_reflect_kernel); MLP in fp32
       es.sm = (float*)mem.alloc((size_t)mb * 76800 * 3 * 4);
+      const int sc[5] = {64, 128, 256, 256, 256};
+      int vh = 240, vw = 320;                      // valid region of the current layer's input
       for (int i = 0; i < 5; ++i) {
-        es.se[i] = (float*)mem.alloc((size_t)mb * sh[i] * sw_[i] * sc[i] * 4);
-        const std::string P = "seg_encoder.model." + std::to_string(i) + ".conv";
-        es.w_se[i] = upload_hwio(mem, sd_get(sd, P + ".weight"));
-        es.b_se[i] = mem.upload(sd_get(sd, P + ".bias").data);
+        const std::string Pn = "seg_encoder.model." + std::to_string(i) + ".conv";
+        const HostTensor& w = sd_get(sd, Pn + ".weight");
+        const HostTensor& bsv = sd_get(sd, Pn + ".bias");
+        int gh, gw, cin_t, kh, kw;
+        const int cin_ref = i == 0 ? 3 : sc[i - 1], cout = sc[i], kk = i == 0 ? 7 : 4;
+        EGN_CHECK(w.shape[0] == cout && w.shape[1] == cin_ref && w.shape[2] == kk && w.shape[3] == kk, Pn + ": unexpected weight shape");
+        if (i == 0) {
+          gh = vh + 6; gw = vw; cin_t = 32; kh = 7; kw = 1;
+          es.st_w[i].assign((size_t)cout * cin_t * 7, 0.f);
+          for (int co = 0; co < cout; ++co)
+            for (int c = 0; c < 3; ++c)
+              for (int dy = 0; dy < 7; ++dy)
+                for (int dx = 0; dx < 7; ++dx)
+                  es.st_w[i][((size_t)co * cin_t + dx * 3 + c) * 7 + dy] = w.data[(((size_t)co * 3 + c) * 7 + dy) * 7 + dx];
+        } else {
+          gh = (vh + 2) / 2; gw = (vw + 2) / 2; cin_t = 4 * cin_ref; kh = 2; kw = 2;
+          es.st_w[i].assign((size_t)cout * cin_t * 4, 0.f);
+          for (int co = 0; co < cout; ++co)
+            for (int c = 0; c < cin_ref; ++c)
+              for (int r = 0; r < 4; ++r)
+                for (int q = 0; q < 4; ++q) {
+                  const int par = (r & 1) * 2 + (q & 1), dy = r >> 1, dx = q >> 1;
+                  es.st_w[i][(((size_t)co * cin_t + par * cin_ref + c) * 2 + dy) * 2 + dx] = w.data[(((size_t)co * cin_ref + c) * 4 + r) * 4 + q];
+                }
+        }
+        es.st_in[i] = new_act(mem, mb, gh, gw, cin_t);
+        es.st_out[i] = new_act(mem, mb, gh, gw, cout);
+        build_conv(es.st_conv[i], mem, Pn, {{es.st_in[i], 0, cin_t, 0}}, {{es.st_w[i].data(), bsv.data.data(), 1, 0}}, cout, cin_t,
+                   kh, kw, gh, gw, mb);
+        set_store_epilogue(es.st_conv[i], es.st_out[i], 0, ACT_RELU);
+        if (i > 0) { vh /= 2; vw /= 2; }
+        es.st_conv[i].flops = 2.0 * cout * cin_ref * kk * kk * vh * vw;
+        finalize_conv(es.st_conv[i]);
+        es.st_w[i].clear(); es.st_w[i].shrink_to_fit();
       }
       es.gap = (float*)mem.alloc((size_t)mb * 256 * 4);
       es.sty = (float*)mem.alloc((size_t)mb * cfg.style_dim * 4);
@@ -889,16 +925,6 @@ struct Engine {
     instnorm_apply_kernel<<<grid, 256, (size_t)Cv * sizeof(float2), st>>>(ap);
     CUDA_OK(cudaGetLastError());
     launches += 1;
-  }
-
-  void conv_f32(const float* in, const float* w, const float* bias, float* out, int B, int Hi, int Wi, int Ci, int Co,
-                int kh, int kw, int stride, int pad, int act, int reflect, cudaStream_t st) {
-    ConvF32Params p;
-    p.in = in; p.w = w; p.bias = bias; p.out = out; p.B = B; p.Hi = Hi; p.Wi = Wi; p.Ci = Ci; p.Co = Co;
-    p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad; p.act = act; p.reflect = reflect;
-    p.Ho = (Hi + 2 * pad - kh) / stride + 1; p.Wo = (Wi + 2 * pad - kw) / stride + 1;
-    launch_1d(conv_f32_kernel, p, (long long)B * p.Ho * p.Wo * Co, st);
-    ++launches;
   }
 
   // x, edge: device fp32 [B][H][W]; logits fp32 [B][3][H][W]; el_out [B][10]; latent [B][153]
@@ -979,12 +1005,23 @@ struct Engine {
           softmax3_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(lp.out, es.sm, nb, (int)hw);
           CUDA_OK(cudaGetLastError()); ++launches;
         }
-        conv_f32(es.sm, es.w_se[0], es.b_se[0], es.se[0], nb, 240, 320, 3, 64, 7, 7, 1, 3, ACT_RELU, 1, st);
-        const int sh[5] = {240, 120, 60, 30, 15}, sw_[5] = {320, 160, 80, 40, 20}, sc[5] = {64, 128, 256, 256, 256};
-        for (int i = 1; i < 5; ++i)
-          conv_f32(es.se[i - 1], es.w_se[i], es.b_se[i], es.se[i], nb, sh[i - 1], sw_[i - 1], sc[i - 1], sc[i], 4, 4, 2, 1,
-                   ACT_RELU, 1, st);
-        gap_f32_kernel<<<nb, 256, 0, st>>>(es.se[4], es.gap, 300, 256); CUDA_OK(cudaGetLastError());
+        {
+          StyleFoldParams fp2;
+          fp2.sm = es.sm; fp2.dst = make_view(*es.st_in[0], 0); fp2.B = nb; fp2.H = 240; fp2.W = 320;
+          launch_1d(style_fold_kernel, fp2, (long long)nb * 246 * 320 * 4, st); ++launches;
+        }
+        run_conv_impl(es.st_conv[0], nb, st);
+        int vh = 240, vw = 320;
+        for (int i = 1; i < 5; ++i) {
+          S2dParams sp;
+          sp.src = make_view(*es.st_out[i - 1], 0); sp.dst = make_view(*es.st_in[i], 0);
+          sp.B = nb; sp.Hg = es.st_out[i - 1]->H; sp.Wg = es.st_out[i - 1]->W; sp.Hs = vh; sp.Ws = vw; sp.C = es.st_out[i - 1]->C;
+          launch_1d(s2d_reflect_kernel, sp, (long long)nb * es.st_in[i]->H * es.st_in[i]->W * 4 * (sp.C / 8), st); ++launches;
+          run_conv_impl(es.st_conv[i], nb, st);
+          vh /= 2; vw /= 2;
+        }
+        gap_act_kernel<<<nb, 256, 0, st>>>(make_view(*es.st_out[4], 0), es.gap, es.st_out[4]->H, es.st_out[4]->W, 15, 20, 256);
+        CUDA_OK(cudaGetLastError());
         linear(es.gap, es.w_se6, es.b_se6, es.sty, nb, 256, cfg.style_dim, 0, st);
         linear(es.sty, es.w_m[0], es.b_m[0], es.m1, nb, cfg.style_dim, 256, 1, st);
         linear(es.m1, es.w_m[1], es.b_m[1], es.m2, nb, 256, 256, 1, st);
