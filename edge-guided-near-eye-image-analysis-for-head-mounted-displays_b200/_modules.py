@@ -48,14 +48,25 @@ class EngineBound(ParamTree):
     def _init_binding(self):
         self._ctx = None
         self._bound_key = None
+        self._items = None
         self.micro_batch = None
 
+    def _apply(self, fn, *a, **k):
+        # .to()/.cuda()/.float() may replace buffer tensors: drop the cached tensor list
+        self._items = None
+        return super()._apply(fn, *a, **k)
+
     def _tensors(self):
-        return list(self.state_dict(keep_vars=True).items())
+        # the tensor objects are stable between _apply calls (load_state_dict copies in place), so the
+        # per-call staleness check is two attribute reads per tensor, not a state_dict() walk - this
+        # sits on the streaming path (batch 1, evaluate.py:112-166)
+        if self._items is None:
+            self._items = list(self.state_dict(keep_vars=True).items())
+        return self._items
 
     def _ensure_ctx(self, device):
         items = self._tensors()
-        key = (str(device), self.micro_batch, tuple((k, t._version, t.data_ptr()) for k, t in items))
+        key = (device, self.micro_batch, tuple([(t._version, t.data_ptr()) for _, t in items]))
         if self._ctx is None or key != self._bound_key:
             if self._ctx is not None:
                 self._ctx.close()

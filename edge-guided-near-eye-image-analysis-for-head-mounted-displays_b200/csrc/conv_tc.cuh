@@ -773,16 +773,27 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 // 4-D map over an NHWC bf16 plane: dims (C, W, H, N), box (32, bw, box_rows, 1), 64-B swizzle.
-static void make_act_map(CUtensorMap* map, const bf16* ptr, int N, int H, int W, int C, int bw, int box_rows) {
+// promo64: the layer reads a channel window of this buffer that does not start/end on 128-byte
+// boundaries, so 128-byte L2 promotion would pull the neighbouring (unread) channels from HBM
+// (measured on enc.down_block1.conv21: 39 MB/frame of DRAM reads for 19.7 MB of operands).
+static void make_act_map(CUtensorMap* map, const bf16* ptr, int N, int H, int W, int C, int bw, int box_rows,
+                         bool promo64 = false) {
   EGN_CHECK(C % 8 == 0, "activation channels must be a multiple of 8");
   EGN_CHECK(box_rows >= 1 && box_rows <= 256, "activation box rows out of range");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
   cuuint32_t box[4] = {EGN_KC, (cuuint32_t)bw, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
+  // tuning knob: L2 promotion of the activation boxes (0 none, 1 64 B, 2 128 B, 3 256 B)
+  static const int promo_env = getenv("EGN_TC_L2PROMO") ? atoi(getenv("EGN_TC_L2PROMO")) : -1;
+  const int promo_sel = promo_env >= 0 ? promo_env : (promo64 ? 1 : 2);
+  const CUtensorMapL2promotion promo = promo_sel == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                       : promo_sel == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                       : promo_sel == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                                        : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
   CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides,
                                box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                               promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   EGN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
 }
 
@@ -820,6 +831,18 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   const int bw = padded(8) < padded(16) ? 8 : 16;
   p.bw_log2 = bw == 8 ? 3 : 4;
   p.sr = 128 / bw;
+  // latency mode (streaming micro-batches of a few frames, evaluate.py's per-image path): when the
+  // planned batch cannot fill the SMs even with single sub-tiles, split N further so that more CTAs
+  // share the layer (each re-reads the activation boxes, which is free while SMs would idle)
+  const int sm_target = 148;
+  auto tiles_at = [&](int S, int n_blocks) {
+    return (long long)ceil_div(g.W, bw) * ceil_div(g.H, S * p.sr) * g.batch * n_blocks;
+  };
+  const bool latency_mode = !getenv("EGN_TC_NO_LATENCY_MODE");
+  while (latency_mode && tiles_at(1, p.n_blocks) * 2 <= sm_target && p.n_tile >= 64 && p.n_tile % 32 == 0) {
+    p.n_blocks *= 2;
+    p.n_tile /= 2;
+  }
   // narrow single-group layers are bound by the shared-memory read of the activation tile (an
   // M=128, N<=64 MMA takes (128+N)/4 cycles, tools/mma_probe.cu): fold hi*hi and hi*lo into one MMA
   p.wide_b = (nsplit == 3 && g.groups == 1 && p.n_tile <= 64) ? 1 : 0;
@@ -835,6 +858,7 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   if (rows_avail >= 4 && 4 * cols <= TC_ACC_STRIDE) p.S = 4;
   if (getenv("EGN_TC_S4SINGLE") && p.wide_b && rows_avail >= 4 && 4 * cols <= 512) p.S = 4;           // tuning knob: one TMEM buffer
   if (const char* e = getenv("EGN_TC_SMAX")) p.S = std::min(p.S, std::max(1, atoi(e)));   // tuning knob
+  while (latency_mode && p.S > 1 && tiles_at(p.S, p.n_blocks) < sm_target) p.S /= 2;      // fewer sub-tiles, more CTAs
   p.tr = p.S * p.sr;
   p.acc_bufs = p.S * cols <= TC_ACC_STRIDE ? 2 : 1;
   p.tiles_x = ceil_div(g.W, bw);

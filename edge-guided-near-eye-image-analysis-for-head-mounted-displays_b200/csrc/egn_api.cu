@@ -164,7 +164,7 @@ int egn_ellipse_refine(egn_ctx* ctx, const uint8_t* argmax_u8, const float* ell_
   API_BEGIN
   EGN_CHECK(ctx && argmax_u8 && ell_norm && out && batch > 0, "bad argument");
   CUDA_OK(cudaSetDevice(ctx->eng.device));
-  dim3 grid(2, batch);
+  dim3 grid(REFINE_CLUSTER, 2, batch);             // one 8-CTA cluster per ellipse (static __cluster_dims__)
   ellipse_refine_kernel<<<grid, REFINE_THREADS, 0, (cudaStream_t)stream>>>(argmax_u8, ell_norm, out, refine);
   CUDA_OK(cudaGetLastError());
   ctx->eng.launches += 1;

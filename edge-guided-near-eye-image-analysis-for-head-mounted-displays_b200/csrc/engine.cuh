@@ -335,8 +335,17 @@ struct Engine {
       tc_configure(L.tc, L.g.cout_pad, nsplit);
       for (int s = 0; s < L.nsrc; ++s) {
         const Act* a = L.src_act[s];
-        make_act_map(&L.tc.a_map[0][s], a->hi, a->N, a->H, a->W, a->C, 1 << L.tc.bw_log2, L.tc.box_rows);
-        make_act_map(&L.tc.a_map[1][s], a->lo, a->N, a->H, a->W, a->C, 1 << L.tc.bw_log2, L.tc.box_rows);
+        // channel window of this source the layer reads: [lo, hi) in 64-byte chunks
+        int lo = a->C, hi = 0;
+        for (int c = 0; c < L.g.nchunks; ++c)
+          if (L.g.chunk_src[c] == s) { lo = std::min(lo, (int)L.g.chunk_c0[c]); hi = std::max(hi, (int)L.g.chunk_c0[c] + EGN_KC); }
+        hi = std::min(hi, a->C);
+        // (only where the operands stream from HBM: at 60x80 and below the buffers are L2-resident and
+        //  the wider promotion is the faster one - measured on enc.down_block3.conv21/conv31)
+        const bool promo64 = a->H * a->W >= 120 * 160 &&
+                             ((lo * 2) % 128 != 0 || ((hi * 2) % 128 != 0 && hi != a->C));
+        make_act_map(&L.tc.a_map[0][s], a->hi, a->N, a->H, a->W, a->C, 1 << L.tc.bw_log2, L.tc.box_rows, promo64);
+        make_act_map(&L.tc.a_map[1][s], a->lo, a->N, a->H, a->W, a->C, 1 << L.tc.bw_log2, L.tc.box_rows, promo64);
       }
       for (int s = L.nsrc; s < EGN_MAX_SRC; ++s) {
         L.tc.a_map[0][s] = L.tc.a_map[0][0];

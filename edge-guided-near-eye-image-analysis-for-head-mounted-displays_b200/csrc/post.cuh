@@ -1,6 +1,8 @@
 // Bandwidth-bound post-processing kernels: segmentation argmax + soft-argmax centres (K6),
 // IoU / centre-error accumulation (K7), ellipse refinement (a12).
 #pragma once
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 #include "common.cuh"
 
 #define POST_SLICES 8     // row slices per frame for the soft-argmax partials
@@ -256,99 +258,147 @@ __device__ inline void ell_transform(const double* p, double sx, double sy, doub
 }
 
 #define REFINE_THREADS 512
+#define REFINE_CLUSTER 8     // CTAs (SMs) that raster one ellipse together
+
+// Shared state of one refinement: three rotating (intersection, area) counter sets - only the ones
+// in the cluster's rank-0 CTA are used - so one cluster barrier per IoU evaluation suffices: set
+// (k+1) % 3 is cleared by rank 0 at the start of evaluation k, after every CTA has passed the barrier
+// of evaluation k-1 and therefore finished reading it (it was last used by evaluation k-2).
+struct RefineShared {
+  int cnt[3][2];
+  int local[2];
+  float e[4], c, s;
+  int box[4];
+};
 
 // IoU of the class mask against the raster of a pixel-space ellipse whose angle is in degrees
 // (utils.py:176-204 with nor=False, angle_nor=True; float32 raster arithmetic like the reference).
-__device__ float ell_iou_block(const uint8_t* __restrict__ seg, int cls, int seg_count, const double* center,
-                               const double* abt, int* sh_cnt) {
-  __shared__ float e[5];
+// The REFINE_CLUSTER CTAs of a thread-block cluster split the rows; the integer counts are reduced
+// through distributed shared memory, so the score is identical in every CTA and bit-identical to a
+// whole-frame raster.
+__device__ float ell_iou_cluster(const uint8_t* __restrict__ seg, int cls, int seg_count, const double* center,
+                                 const double* abt, RefineShared* sh, int& eval) {
+  cg::cluster_group cl = cg::this_cluster();
+  const int rank = (int)cl.block_rank();
+  const int k = eval % 3;
+  ++eval;
   if (threadIdx.x == 0) {
     double p[5] = {center[0], center[1], abt[0], abt[1], abt[2] / 180.0 * 3.14159};
     double o[5];
     ell_transform(p, 2.0 / EGN_W, 2.0 / EGN_H, -1.0, -1.0, o);
-    e[0] = (float)o[0]; e[1] = (float)o[1]; e[2] = (float)o[2]; e[3] = (float)o[3];
-    e[4] = (float)o[4];
-    sh_cnt[0] = 0; sh_cnt[1] = 0;
+    sh->e[0] = (float)o[0]; sh->e[1] = (float)o[1]; sh->e[2] = (float)o[2]; sh->e[3] = (float)o[3];
     // cos / sin are taken in double by the reference and then used as python floats
-    const double cc = cos(o[4]), ss = sin(o[4]);
-    reinterpret_cast<float*>(sh_cnt)[2] = (float)cc;
-    reinterpret_cast<float*>(sh_cnt)[3] = (float)ss;
+    sh->c = (float)cos(o[4]); sh->s = (float)sin(o[4]);
+    sh->local[0] = 0; sh->local[1] = 0;
+    if (rank == 0) { sh->cnt[(k + 1) % 3][0] = 0; sh->cnt[(k + 1) % 3][1] = 0; }
+    // Only pixels inside the ellipse count (area, intersection), so the raster is restricted to a
+    // conservative pixel-space bounding box: centre +- (1.01 * max(|a|, |b|) + 3) - the meshgrid maps
+    // pixel x to x * W / (W - 1) in the ellipse's pixel frame, a stretch below 0.5 %.  Non-finite or
+    // huge parameters fall back to the whole frame, which is what the reference rasterises.
+    int bx0 = 0, bx1 = EGN_W, by0 = 0, by1 = EGN_H;
+    const double r = 1.01 * fmax(fabs(abt[0]), fabs(abt[1])) + 3.0;
+    if (r < 1.0e6 && fabs(center[0]) < 1.0e6 && fabs(center[1]) < 1.0e6) {   // false for NaN / inf
+      bx0 = max(0, min(EGN_W, (int)floor(center[0] - r))); bx1 = max(bx0, min(EGN_W, (int)ceil(center[0] + r) + 1));
+      by0 = max(0, min(EGN_H, (int)floor(center[1] - r))); by1 = max(by0, min(EGN_H, (int)ceil(center[1] + r) + 1));
+    }
+    sh->box[0] = bx0; sh->box[1] = bx1; sh->box[2] = by0; sh->box[3] = by1;
   }
   __syncthreads();
-  const float ex = e[0], ey = e[1], ea = e[2], eb = e[3];
-  const float c = reinterpret_cast<float*>(sh_cnt)[2], s = reinterpret_cast<float*>(sh_cnt)[3];
+  const float ex = sh->e[0], ey = sh->e[1], ea = sh->e[2], eb = sh->e[3], c = sh->c, s = sh->s;
+  const int bx0 = sh->box[0], bx1 = sh->box[1], by0 = sh->box[2], by1 = sh->box[3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int inter = 0, area = 0;
-  for (int i = threadIdx.x; i < EGN_H * EGN_W; i += REFINE_THREADS) {
-    const int y = i / EGN_W, x = i % EGN_W;
-    const float mx = linspace_m11(x, EGN_W), my = linspace_m11(y, EGN_H);
-    const float X = __fadd_rn(__fmul_rn(mx - ex, c), __fmul_rn(my - ey, s));
-    const float Y = __fadd_rn(__fmul_rn(-(mx - ex), s), __fmul_rn(my - ey, c));
-    const float qx = X / ea, qy = Y / eb;
-    const float wt = __fadd_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)), -1.0f);
-    if (wt <= 0.f) { ++area; inter += (seg[i] == cls); }
+  // one image row per warp at a time, rows interleaved over the cluster's CTAs
+  for (int y = by0 + rank * (REFINE_THREADS / 32) + warp; y < by1; y += REFINE_CLUSTER * (REFINE_THREADS / 32)) {
+    const float my = linspace_m11(y, EGN_H);
+    const float dys = __fmul_rn(my - ey, s), dyc = __fmul_rn(my - ey, c);
+    const uint8_t* row = seg + y * EGN_W;
+    for (int x = bx0 + lane; x < bx1; x += 32) {
+      const float mx = linspace_m11(x, EGN_W);
+      const float X = __fadd_rn(__fmul_rn(mx - ex, c), dys);
+      const float Y = __fadd_rn(__fmul_rn(-(mx - ex), s), dyc);
+      const float qx = X / ea, qy = Y / eb;
+      const float wt = __fadd_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)), -1.0f);
+      if (wt <= 0.f) { ++area; inter += (row[x] == cls); }
+    }
   }
   for (int o = 16; o > 0; o >>= 1) {
     inter += __shfl_xor_sync(0xffffffffu, inter, o);
     area += __shfl_xor_sync(0xffffffffu, area, o);
   }
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&sh_cnt[0], inter); atomicAdd(&sh_cnt[1], area); }
+  if (lane == 0 && (inter | area)) { atomicAdd(&sh->local[0], inter); atomicAdd(&sh->local[1], area); }
   __syncthreads();
-  const float I = (float)sh_cnt[0], A = (float)sh_cnt[1];
-  const float score = I / (((float)seg_count + A) - I);
-  __syncthreads();
-  return score;
+  RefineShared* r0 = cl.map_shared_rank(sh, 0);
+  if (threadIdx.x == 0 && (sh->local[0] | sh->local[1])) {
+    atomicAdd(&r0->cnt[k][0], sh->local[0]);
+    atomicAdd(&r0->cnt[k][1], sh->local[1]);
+  }
+  cl.sync();
+  const float I = (float)r0->cnt[k][0], A = (float)r0->cnt[k][1];
+  return I / (((float)seg_count + A) - I);
 }
 
 // ell_norm: [B][2][5] normalised (iris, pupil) ellipses (elPred); out: [B][2][5] refined pixel ellipses
-// (cx, cy, a, b, theta_rad), iris first.  grid = (2, B).
-__global__ void __launch_bounds__(REFINE_THREADS) ellipse_refine_kernel(const uint8_t* __restrict__ argmax,
-                                                                         const float* __restrict__ ell_norm,
-                                                                         double* __restrict__ out, int do_refine) {
-  const int which = blockIdx.x, n = blockIdx.y;
+// (cx, cy, a, b, theta_rad), iris first.  grid = (REFINE_CLUSTER, 2, B), one cluster per ellipse.
+__global__ void __cluster_dims__(REFINE_CLUSTER, 1, 1) __launch_bounds__(REFINE_THREADS)
+ellipse_refine_kernel(const uint8_t* __restrict__ argmax, const float* __restrict__ ell_norm,
+                      double* __restrict__ out, int do_refine) {
+  cg::cluster_group cl = cg::this_cluster();
+  const int which = blockIdx.y, n = blockIdx.z;
   const int cls = which == 0 ? 1 : 2;             // iris mask == 1, pupil mask == 2 (evaluate.py:148-151)
   const uint8_t* seg = argmax + (size_t)n * EGN_H * EGN_W;
-  __shared__ int sh_cnt[4];
+  __shared__ RefineShared sh;
   __shared__ int sh_seg;
   __shared__ double px[5];
   if (threadIdx.x == 0) {
     sh_seg = 0;
+    for (int i = 0; i < 3; ++i) { sh.cnt[i][0] = 0; sh.cnt[i][1] = 0; }
     double p[5];
     for (int i = 0; i < 5; ++i) p[i] = (double)ell_norm[((size_t)n * 2 + which) * 5 + i];
     ell_transform(p, EGN_W / 2.0, EGN_H / 2.0, EGN_W / 2.0, EGN_H / 2.0, px);
   }
   __syncthreads();
   int cnt = 0;
-  for (int i = threadIdx.x; i < EGN_H * EGN_W; i += REFINE_THREADS) cnt += (seg[i] == cls);
+  {
+    const uint32_t* seg4 = reinterpret_cast<const uint32_t*>(seg);
+    const uint32_t pat = 0x01010101u * (uint32_t)cls;
+    for (int i = threadIdx.x; i < EGN_H * EGN_W / 4; i += REFINE_THREADS) {
+      const uint32_t d = __ldg(seg4 + i) ^ pat;       // a byte equals cls <=> its xor is 0
+      cnt += ((d & 0xffu) == 0) + ((d & 0xff00u) == 0) + ((d & 0xff0000u) == 0) + ((d & 0xff000000u) == 0);
+    }
+  }
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if ((threadIdx.x & 31) == 0) atomicAdd(&sh_seg, cnt);
-  __syncthreads();
+  cl.sync();                                       // counters of every CTA are initialised
   const int seg_count = sh_seg;
   double center[2] = {px[0], px[1]};
   double now[3] = {px[2], px[3], px[4] * 180.0 / 3.14159};
   if (do_refine) {
-    float rt = ell_iou_block(seg, cls, seg_count, center, now, sh_cnt);
+    int eval = 0;
+    float rt = ell_iou_cluster(seg, cls, seg_count, center, now, &sh, eval);
     double d[3] = {1.0, 1.0, 1.0};
     for (int tt = 0; tt < 40; ++tt) {
       bool flag = false;
       for (int j = 0; j < 3; ++j) {
         now[j] -= d[j];
-        float sc = ell_iou_block(seg, cls, seg_count, center, now, sh_cnt);
+        float sc = ell_iou_cluster(seg, cls, seg_count, center, now, &sh, eval);
         if (sc > rt) { flag = true; continue; }
         now[j] += 2.0 * d[j];
-        sc = ell_iou_block(seg, cls, seg_count, center, now, sh_cnt);
+        sc = ell_iou_cluster(seg, cls, seg_count, center, now, &sh, eval);
         if (sc > rt) { flag = true; continue; }
         now[j] -= d[j];
         d[j] *= 0.8;
       }
-      const float sc = ell_iou_block(seg, cls, seg_count, center, now, sh_cnt);
+      const float sc = ell_iou_cluster(seg, cls, seg_count, center, now, &sh, eval);
       if (sc > rt) rt = sc;
       if (!flag) break;
     }
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && cl.block_rank() == 0) {
     double* o = out + ((size_t)n * 2 + which) * 5;
     o[0] = center[0]; o[1] = center[1]; o[2] = now[0]; o[3] = now[1]; o[4] = now[2] / 180.0 * 3.14159;
   }
+  cl.sync();                                       // no CTA exits while a peer may still read its shared memory
 }
 
 

@@ -291,3 +291,28 @@ def test_real_frames_batch_parity(env):
         assert np.abs((ep.cpu().numpy()[:, sl] - ref["elPred"].numpy()[:, sl]) * scale).max() < 0.25
     par = [2, 3, 4, 7, 8, 9]
     assert rel_err(eo.cpu().numpy()[:, par], ref["elOut"].numpy()[:, par]) < 1e-2
+
+
+def test_throughput_tiling_parity(env, monkeypatch):
+    """The small micro-batches of these tests plan the convolutions in latency mode (more, smaller
+    CTA tiles); bench.py's micro-batch of 64 frames uses the throughput tiling.  EGN_TC_NO_LATENCY_MODE
+    pins that tiling at a small batch so the exact kernel configuration that is benchmarked meets the
+    same parity bars, end to end (BDCN edge -> ESF-Net -> argmax / centres / ellipse parameters)."""
+    monkeypatch.setenv("EGN_TC_NO_LATENCY_MODE", "1")
+    egn, g, dev = env["egn"], env["graph"], env["dev"]
+    em = egn.BDCN(); em.load_state_dict(env["bsd"]); em = em.cuda().eval(); em.micro_batch = 2
+    m, st, esd = _model(env, "baseline_edge", mb=2)
+    gold = np.load(os.path.join(env["golden"], "fwd_baseline_edge.npz"))
+    with torch.no_grad():
+        e = em.edge(env["img"].to(dev))
+        lo, eo, la, am, ep = m.infer(env["img"].to(dev), e, None)
+    np.testing.assert_allclose(e.cpu().numpy(), gold["edge"], atol=5e-4)
+    assert (am.cpu().numpy() == gold["pred"]).mean() >= 0.999
+    scale = np.array([160.0, 120.0])
+    for sl in (slice(0, 2), slice(5, 7)):
+        assert np.abs((ep.cpu().numpy()[:, sl] - gold["elPred"][:, sl]) * scale).max() < 0.25
+    par = [2, 3, 4, 7, 8, 9]
+    assert rel_err(eo.cpu().numpy()[:, par], gold["elOut"][:, par]) < 1e-2
+    for layer in ["features.conv4_2", "features.conv5_1", "msblock4_1.conv"]:
+        d, r = em.context(dev).conv_selfcheck(layer, 2)
+        assert d <= 1e-4 * max(r, 1.0), (layer, d, r)
