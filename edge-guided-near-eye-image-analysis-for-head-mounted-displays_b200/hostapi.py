@@ -101,6 +101,65 @@ def evaluate_batch(model, edge_model, batch, accumulator, args=None):
     return logits, el_pred, el_out, argmax
 
 
+def summarize_batches(acc_rows):
+    """Reduces per-batch accumulator rows [nbatches,16] the way test.calc_acc does (test.py:215-252):
+    per batch the nanmean over samples of each class IoU / each centre distance (what getSeg_metrics
+    and getPoint_metric return, utils.py:120-162), then nanmean over batches, then the mean of the three
+    class IoUs.  Returns (ious[3], pupil_latent, iris_latent, pupil_seg, iris_seg)."""
+    a = np.asarray(acc_rows, dtype=np.float64).reshape(-1, 16)
+    with np.errstate(all="ignore"):
+        iou_b = np.where(a[:, 3:6] > 0, a[:, 0:3] / a[:, 3:6], np.nan)
+        dist_b = np.where(a[:, 10:14] > 0, a[:, 6:10] / a[:, 10:14], np.nan)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", category=RuntimeWarning)
+            ious = np.nanmean(iou_b, axis=0)
+            d = np.nanmean(dist_b, axis=0)
+    return ious, float(d[0]), float(d[1]), float(d[2]), float(d[3])
+
+
+def calc_acc(args, testloader, model, edge_model, device, return_all=False, disp=0, iou_by_sample_out=None):
+    """Drop-in for test.calc_acc (test.py:32-252) on the engine: same loop over the DataLoader's
+    9-tuples, same prints, same return values - but edge, forward, argmax, centres and the per-sample
+    Jaccard / centre-distance metrics all stay on the device; one small D2H of the per-batch
+    accumulators happens after the last batch.  ``iou_by_sample_out`` (a list) receives the per-sample
+    IoUs [B,3] of every batch, the data test.py:219-230 pickles when args.record_iou == 1."""
+    model.eval()
+    dev = torch.device(device)
+    rows, by_sample = [], []
+    with torch.no_grad():
+        for bt, batchdata in enumerate(testloader):
+            if getattr(args, "test_normal", False) and bt > 10:
+                break
+            acc = MetricAccumulator(dev)
+            img, labels, spatW, distMap, pupil_center, iris_center, elNorm, cond, imInfo = batchdata
+            edge = calc_edge(args, img, edge_model, dev)
+            cond_d = cond.to(dev, torch.float32)
+            logits, el_out, latent, argmax, el_pred = model.infer(img.to(dev), edge, cond_d)
+            lab = labels.to(dev)
+            if lab.dtype not in (torch.uint8, torch.int64):
+                lab = lab.to(torch.int64)
+            by = torch.empty((img.shape[0], 3), dtype=torch.float32, device=dev) \
+                if (iou_by_sample_out is not None or getattr(args, "record_iou", 0) == 1) else None
+            model.context(dev).metrics_accumulate(argmax, lab.contiguous(), cond_d, acc.acc, pupil_center.to(dev),
+                                                  iris_center.to(dev), el_out, el_pred, by)
+            rows.append(acc.acc)
+            if by is not None:
+                by_sample.append(by)
+    a = torch.stack(rows).cpu().numpy() if rows else np.zeros((0, 16))
+    ious, d_pl, d_il, d_ps, d_is = summarize_batches(a)
+    if iou_by_sample_out is not None:
+        iou_by_sample_out.extend(b.cpu().numpy() for b in by_sample)
+    print('mIoU: {}. IoUs: {}'.format(np.mean(ious), ious))
+    print('Latent space PUPIL dist. Mean: {}'.format(d_pl))
+    print('Segmentation PUPIL dist. Mean: {}'.format(d_ps))
+    print('Latent space IRIS dist. Mean: {}'.format(d_il))
+    print('Segmentation IRIS dist. Mean: {}'.format(d_is))
+    if return_all:
+        return ious, d_pl, d_il, d_ps, d_is
+    return np.mean(ious), d_pl, d_il
+
+
 def evaluate_ellseg_on_image(frame, model, edge_model, device=None, refine=True):
     """evaluate.py:112-166: edge, forward, argmax, normalised->pixel ellipses and the IoU
     refinement, returning (edge_map, seg_map, pupil_ellipse, iris_ellipse) as numpy arrays.

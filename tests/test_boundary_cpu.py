@@ -172,3 +172,35 @@ def test_metric_all_reduce_gloo_world2():
         assert r["frames"] == 10
         np.testing.assert_allclose(r["IoUs"], [0.55, 0.275, 0.55 / 3], rtol=1e-12)
         assert r["pupil_latent_px"] == pytest.approx(4.5)
+
+
+def test_summarize_batches_matches_calc_acc_aggregation():
+    """test.py:215-252 aggregates nanmean-over-batches of per-batch nanmeans (utils.py:120-162); the
+    host reduction of the per-batch device accumulators must reproduce that, including batches where
+    a class never occurs in the ground truth and batches without valid samples."""
+    rng = np.random.default_rng(3)
+    rows, iou_b, dist_b = [], [], []
+    for b in range(5):
+        n = int(rng.integers(1, 6))
+        s = rng.random((n, 3))
+        s[rng.random((n, 3)) < 0.3] = np.nan                 # class absent from GT -> NaN (getSeg_metrics)
+        if b == 2:
+            s[:] = np.nan                                     # no valid sample in this batch
+        d = rng.random((n, 4)) * 10
+        valid = rng.random((n, 4)) < 0.8
+        a = np.zeros(16)
+        a[0:3] = np.nansum(s, 0); a[3:6] = np.isfinite(s).sum(0)
+        a[6:10] = (d * valid).sum(0); a[10:14] = valid.sum(0); a[14] = n
+        rows.append(a)
+        with np.errstate(all="ignore"):
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", category=RuntimeWarning)
+                iou_b.append(np.nanmean(s, 0))
+            dist_b.append(np.where(valid.sum(0) > 0, (d * valid).sum(0) / np.maximum(valid.sum(0), 1), np.nan))
+    ious, pl, il, ps, isg = egn_b200.summarize_batches(np.stack(rows))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", category=RuntimeWarning)
+        np.testing.assert_allclose(ious, np.nanmean(np.stack(iou_b), 0), rtol=1e-12)
+        np.testing.assert_allclose([pl, il, ps, isg], np.nanmean(np.stack(dist_b), 0), rtol=1e-12)

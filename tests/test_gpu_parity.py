@@ -316,3 +316,36 @@ def test_throughput_tiling_parity(env, monkeypatch):
     for layer in ["features.conv4_2", "features.conv5_1", "msblock4_1.conv"]:
         d, r = em.context(dev).conv_selfcheck(layer, 2)
         assert d <= 1e-4 * max(r, 1.0), (layer, d, r)
+
+
+def test_calc_acc_mirror_on_synthetic_loader(env, capsys):
+    """egn_b200.calc_acc (the test.calc_acc mirror, test.py:32-252) over a two-batch loader with
+    unequal batch sizes against the oracle's per-batch metrics aggregated the reference's way."""
+    egn, g, synth, dev = env["egn"], env["graph"], env["synth"], env["dev"]
+    m, st, esd = _model(env, "baseline_edge")
+    keys = ("img", "label", "spatW", "distMap", "pupil_center", "iris_center", "elNorm", "cond", "imInfo")
+    loader = []
+    for start, n in ((200, 3), (300, 2)):
+        eb = synth.synthetic_eye_batch(start, n)
+        loader.append(tuple(torch.from_numpy(eb[k]) for k in keys))
+    by = []
+    out = egn.calc_acc(None, loader, m, env["edge_model"], dev, return_all=True, iou_by_sample_out=by)
+    printed = capsys.readouterr().out
+    assert "mIoU:" in printed and "Segmentation PUPIL dist. Mean:" in printed
+    ious_b, dpl, dil, dps, dis = [], [], [], [], []
+    with torch.no_grad():
+        for batch in loader:
+            e_ref = g.calc_edge(env["bsd"], batch[0])
+            ref = g.esf_forward(esd, st, batch[0], e_ref)
+            pref = g.get_predictions(ref["op"]).numpy()
+            c = batch[7].numpy()
+            ious_b.append(g.seg_metrics(batch[1].numpy(), pref, c[:, 1])[1])
+            dpl.append(g.point_metric(batch[4].numpy(), ref["elOut"][:, 5:7].numpy(), c[:, 0], (240, 320))[0])
+            dil.append(g.point_metric(batch[5].numpy(), ref["elOut"][:, 0:2].numpy(), c[:, 1], (240, 320))[0])
+            dps.append(g.point_metric(batch[4].numpy(), ref["elPred"][:, 5:7].numpy(), c[:, 1], (240, 320))[0])
+            dis.append(g.point_metric(batch[5].numpy(), ref["elPred"][:, 0:2].numpy(), c[:, 1], (240, 320))[0])
+    ious_ref = np.nanmean(np.stack(ious_b), 0)
+    assert np.abs(out[0] - ious_ref).max() * 100 < 0.1                      # mIoU within 0.1 pt, per class
+    for got, want in zip(out[1:], (dpl, dil, dps, dis)):
+        assert abs(got - np.nanmean(want)) < 0.25                            # centres within 0.25 px
+    assert len(by) == 2 and by[0].shape == (3, 3) and by[1].shape == (2, 3)

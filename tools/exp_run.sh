@@ -1,6 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python tools/stream_bench.py --out gpurun_out/x4_stream.json > gpurun_out/x4_stream.log 2>&1
-python tools/stream_bench.py --no-refine --out gpurun_out/x4_stream_norefine.json > gpurun_out/x4_stream_norefine.log 2>&1
-python bench.py --batch 64 --micro-batch 64 --steps 2 --warmup 3 --no-cpu-baseline --layer-table gpurun_out/x4_layers.csv > gpurun_out/x4_bench.json 2>/dev/null
-cut -c1-200 gpurun_out/x4_stream.log; cut -c1-200 gpurun_out/x4_stream_norefine.log; cut -c1-120 gpurun_out/x4_bench.json
+timeout 600 python -m pytest tests -m gpu -x -q -k "calc_acc or throughput or metrics" 2>&1 | tail -3
+bash tools/sweep.sh 1 gpurun_out/x6_sweep_n1.jsonl 64 256 1024 4096
+tail -3 gpurun_out/x6_sweep_n1.jsonl.err
