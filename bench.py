@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="egn", choices=["egn", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
-    ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("EGN_MICRO_BATCH", "64")))
+    ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("EGN_MICRO_BATCH", "128")))
     ap.add_argument("--config", default="baseline_edge")
     ap.add_argument("--cpu-frames", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -94,7 +94,7 @@ static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 #define EGN_MAX_SRC 4
 #define EGN_KC 32  // channels per K chunk (64-byte swizzled rows)
 
-enum ConvMode { CONV_STORE = 0, CONV_MSBLOCK = 1 };
+enum ConvMode { CONV_STORE = 0, CONV_MSBLOCK = 1, CONV_LOGITS = 2 };
 
 struct ConvGeom {
   int H, W, batch;            // output == input spatial size (stride 1, "same" padding)
@@ -132,4 +132,8 @@ struct ConvEpi {
   const float* score_w;    // [2][32]
   float* score;            // [N][H][W][2]
   int score_accum;
+  // CONV_LOGITS: the first logits_c channels go to an fp32 NCHW tensor [N][logits_c][H][W] (the
+  // segmentation logits the reference returns, models/RITnet_v2.py:288) instead of a split-bf16 buffer
+  float* logits;
+  int logits_c;
 };

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(ST_THREADS) conv_simt_kernel(const SimtParams 
   const int lin = p0 + px;
   const bool valid = lin < HW;
   const size_t pix = (size_t)n * HW + lin;
-  if (p.e.mode == CONV_STORE) {
+  if (p.e.mode == CONV_STORE || p.e.mode == CONV_LOGITS) {
     const int ch = cb + cog * 8;
     if (valid && ch + 8 <= p.e.cout_store) {
       float v[8];
@@ -102,6 +102,11 @@ __global__ void __launch_bounds__(ST_THREADS) conv_simt_kernel(const SimtParams 
         if (p.e.post_scale) a = a * p.e.post_scale[ch + i] + p.e.post_shift[ch + i];
         v[i] = a;
       }
+      if (p.e.mode == CONV_LOGITS) {
+        if (ch == 0)
+          for (int i = 0; i < p.e.logits_c && i < 8; ++i)
+            p.e.logits[((size_t)n * p.e.logits_c + i) * HW + lin] = v[i];
+      } else
       store8(p.e.out_hi, p.e.out_lo, pix * p.e.out_C + p.e.out_coff + ch, v);
       if (p.e.stats) {
 #pragma unroll

@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * TC_ACC_STRIDE;
 
       if (p.dbg & 1) {
-      } else if (p.e.mode == CONV_STORE) {
+      } else if (p.e.mode == CONV_STORE || p.e.mode == CONV_LOGITS) {
         const int per_sub = p.n_tile >> 4;         // 16-column groups per sub-tile
         const bool has_post = p.e.post_scale != nullptr;
         for (int g = half; g < per_sub; g += 2) {   // a warp keeps its channel groups across sub-tiles
@@ -669,7 +669,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                   for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], c_scale[cb + i], c_shift[cb + i]);
                 }
-                if (valid) store16(p.e.out_hi, p.e.out_lo, pix * p.e.out_C + p.e.out_coff + cb, v);
+                if (p.e.mode == CONV_LOGITS) {
+                  if (valid && cb == 0) {
+                    float* dst = p.e.logits + (size_t)n * p.e.logits_c * p.g.H * p.g.W + (size_t)py * p.g.W + px;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                      if (i < p.e.logits_c) dst[(size_t)i * p.g.H * p.g.W] = v[i];
+                  }
+                } else if (valid) store16(p.e.out_hi, p.e.out_lo, pix * p.e.out_C + p.e.out_coff + cb, v);
                 if (p.e.stats) {
                   const float mk = valid ? 1.f : 0.f;
 #pragma unroll

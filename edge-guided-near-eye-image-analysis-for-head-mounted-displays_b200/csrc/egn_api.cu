@@ -55,6 +55,9 @@ int egn_create(int device, const egn_config* cfg, egn_ctx** out) {
   c->eng.nsplit = ns ? atoi(ns) : 3;
   EGN_CHECK(c->eng.nsplit == 1 || c->eng.nsplit == 3, "EGN_NSPLIT must be 1 or 3");
   c->eng.err_flag = (int*)c->eng.mem_misc.alloc(sizeof(int));
+  if (const char* fg = getenv("EGN_L2_FETCH")) {      // tuning knob: L2 fetch granularity hint (32 / 64 / 128 bytes)
+    CUDA_OK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg)));
+  }
   *out = c.release();
   API_END
 }
@@ -289,6 +292,7 @@ int egn_conv_selfcheck(egn_ctx* ctx, const char* layer, int frames, double* max_
   const int n = std::min(frames, L.g.batch);
   const size_t px = (size_t)n * L.g.H * L.g.W;
   std::vector<float> a, b;
+  float* logits_scratch = nullptr;
   auto fetch = [&](std::vector<float>& v) {
     CUDA_OK(cudaDeviceSynchronize());
     if (L.e.mode == CONV_STORE) {
@@ -302,11 +306,18 @@ int egn_conv_selfcheck(egn_ctx* ctx, const char* layer, int frames, double* max_
           const size_t i = p * L.e.out_C + L.e.out_coff + c;
           v[p * L.e.cout_store + c] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
         }
+    } else if (L.e.mode == CONV_LOGITS) {
+      v.resize(px * L.e.logits_c);
+      CUDA_OK(cudaMemcpy(v.data(), logits_scratch, v.size() * sizeof(float), cudaMemcpyDeviceToHost));
     } else {
       v.resize(px * 2);
       CUDA_OK(cudaMemcpy(v.data(), L.e.score, px * 2 * sizeof(float), cudaMemcpyDeviceToHost));
     }
   };
+  if (L.e.mode == CONV_LOGITS) {     // the logits tensor belongs to the caller: run both kernels into a scratch copy
+    CUDA_OK(cudaMalloc(&logits_scratch, px * L.e.logits_c * sizeof(float)));
+    L.tc.e.logits = logits_scratch; L.simt.e.logits = logits_scratch;
+  }
   TcParams tp = L.tc;
   tp.g.batch = n; tp.total_tiles = tp.tiles_x * tp.tiles_y * n * tp.n_blocks; tp.e.score_accum = 0;
   tc_launch(tp, e.num_sms, 0);
@@ -322,6 +333,10 @@ int egn_conv_selfcheck(egn_ctx* ctx, const char* layer, int frames, double* max_
     if (a[i] != a[i]) md = 1e30;
   }
   *max_diff = md; *max_ref = mr;
+  if (logits_scratch) {
+    L.tc.e.logits = nullptr; L.simt.e.logits = nullptr;
+    cudaFree(logits_scratch);
+  }
   API_END
 }
 

@@ -167,7 +167,7 @@ struct Engine {
     int E = 0;                    // encoder frames per micro-batch
     Act *h1, *bt, *fin;
     FirstConvParams first;
-    ConvLayer head2, final1;
+    ConvLayer head2, final1, final2;
     Block blk[5];
     UpBlock up[4];
     LastConvParams last;
@@ -802,6 +802,18 @@ struct Engine {
       for (int co = 0; co < 3; ++co)
         for (int c = 0; c < 32; ++c)
           for (int t = 0; t < 9; ++t) wp[((size_t)t * 32 + c) * 3 + co] = w2.data[((size_t)co * 32 + c) * 9 + t];
+      {
+        // conv2 (32 -> 3) + lrelu + BN on the tensor cores too: N = 16 tile (3 live columns), fp32 NCHW logits
+        build_conv(es.final2, mem, "dec.final.conv2", {{es.fin, 0, 32, 0}}, {{w2.data.data(), b2.data.data(), 1, 1}}, 3, 32,
+                   3, 3, 240, 320, mb);
+        std::vector<float> sh16;
+        std::vector<float> sc16 = bn_scale(sd, "dec.final.bn", 3, es.final2.g.cout_pad, sh16);
+        ConvEpi& e = es.final2.e;
+        e.mode = CONV_LOGITS; e.act = ACT_LRELU; e.cout_store = es.final2.g.cout_pad;
+        e.post_scale = mem.upload(sc16); e.post_shift = mem.upload(sh16);
+        e.logits = nullptr; e.logits_c = 3;
+        finalize_conv(es.final2);
+      }
       std::vector<float> shift;
       std::vector<float> scale = bn_scale(sd, "dec.final.bn", 3, 3, shift);
       es.last.src = make_view(*es.fin, 0);
@@ -1003,10 +1015,16 @@ struct Engine {
       run_conv(es.final1, nb, st);
       LastConvParams lp = es.last;
       lp.B = nb; lp.out = logits + (size_t)b0 * 3 * hw;
-      aux("esf.last_conv", st, [&] {
-        last_conv_kernel<<<dim3(EGN_W / LAST_TILE, EGN_H / LAST_TILE, nb), 256, 0, st>>>(lp);
-        CUDA_OK(cudaGetLastError()); ++launches;
-      });
+      static const bool last_simt = getenv("EGN_LAST_SIMT") != nullptr;     // tuning knob: the fp32 CUDA-core kernel
+      if (last_simt) {
+        aux("esf.last_conv", st, [&] {
+          last_conv_kernel<<<dim3(EGN_W / LAST_TILE, EGN_H / LAST_TILE, nb), 256, 0, st>>>(lp);
+          CUDA_OK(cudaGetLastError()); ++launches;
+        });
+      } else {
+        es.final2.tc.e.logits = lp.out; es.final2.simt.e.logits = lp.out;
+        run_conv(es.final2, nb, st);
+      }
       // ---- AdaIN parameters from the softmaxed segmentation (RITnet_v2.py:289-308)
       if (cfg.add_seg) {
         {

@@ -116,7 +116,7 @@ def test_esf_tensor_core_layers_match_simt(env):
     ctx = m.context(dev)
     for layer in ["enc.head.conv2", "enc.down_block1.conv21", "enc.down_block2.conv31", "enc.down_block3.conv1",
                   "enc.bottleneck.TD.conv", "dec.up_block4.conv21", "dec.up_block3.conv11", "dec.up_block1.conv22",
-                  "dec.final.conv1", "elReg.c1"]:
+                  "dec.final.conv1", "dec.final.conv2", "elReg.c1"]:
         d, r = ctx.conv_selfcheck(layer, 2)
         assert d <= 1e-4 * max(r, 1.0), (layer, d, r)
 
