@@ -14,7 +14,7 @@ class EgnConfig(ctypes.Structure):
 
 EXPORTS = ["egn_last_error", "egn_version", "egn_create", "egn_destroy", "egn_set_weights", "egn_plan",
            "egn_bdcn_forward", "egn_esf_forward", "egn_seg_post", "egn_metrics_accumulate",
-           "egn_ellipse_refine", "egn_preprocess_u8", "egn_launch_count", "egn_flops_per_frame", "egn_debug_read",
+           "egn_ellipse_refine", "egn_preprocess_u8", "egn_forward_loss", "egn_launch_count", "egn_flops_per_frame", "egn_debug_read",
            "egn_conv_selfcheck", "egn_profile", "egn_profile_read", "egn_profile_table"]
 
 _lib = None
@@ -45,6 +45,7 @@ def load():
     lib.egn_seg_post.argtypes = [vp, vp, vp, vp, vp, vp, ci, vp]
     lib.egn_metrics_accumulate.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, ci, vp]
     lib.egn_ellipse_refine.argtypes = [vp, vp, vp, vp, ci, ci, vp]
+    lib.egn_forward_loss.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, ctypes.c_float, vp, ci, vp]
     lib.egn_preprocess_u8.argtypes = [vp, vp, vp, ci, vp]
     lib.egn_launch_count.argtypes = [vp]
     lib.egn_launch_count.restype = cll

@@ -9,6 +9,8 @@ struct egn_ctx {
   int partial_cap = 0;
   int* counts = nullptr;
   int counts_cap = 0;
+  double* loss_partial = nullptr;
+  int loss_cap = 0;
 };
 
 static thread_local std::string g_err;
@@ -157,6 +159,28 @@ int egn_metrics_accumulate(egn_ctx* ctx, const uint8_t* argmax_u8, const void* l
   CUDA_OK(cudaGetLastError());
   metrics_finish_kernel<<<(batch + 127) / 128, 128, 0, st>>>(ctx->counts, cond, pupil_c, iris_c, el_out, el_pred, acc,
                                                              iou_by_sample, batch);
+  CUDA_OK(cudaGetLastError());
+  ctx->eng.launches += 2;
+  API_END
+}
+
+int egn_forward_loss(egn_ctx* ctx, const float* logits, const void* target, int target_is_i64, const float* spat_w,
+                     const float* dist_map, const float* cond, const float* pupil_c, const float* el_norm,
+                     const float* el_out, const float* el_pred, float alpha, float* loss, int batch, void* stream) {
+  API_BEGIN
+  EGN_CHECK(ctx && logits && target && spat_w && dist_map && cond && pupil_c && el_norm && el_out && el_pred && loss &&
+                batch > 0, "bad argument");
+  CUDA_OK(cudaSetDevice(ctx->eng.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ctx->loss_cap < batch) {
+    ctx->loss_partial = (double*)ctx->eng.mem_misc.alloc((size_t)batch * LOSS_SLICES * LOSS_TERMS * sizeof(double));
+    ctx->loss_cap = batch;
+  }
+  dim3 grid(LOSS_SLICES, batch);
+  seg_loss_kernel<<<grid, 256, 0, st>>>(logits, (const uint8_t*)target, target_is_i64 ? 8 : 1, spat_w, dist_map,
+                                        ctx->loss_partial);
+  CUDA_OK(cudaGetLastError());
+  seg_loss_finish_kernel<<<1, 256, 0, st>>>(ctx->loss_partial, cond, pupil_c, el_norm, el_out, el_pred, alpha, loss, batch);
   CUDA_OK(cudaGetLastError());
   ctx->eng.launches += 2;
   API_END

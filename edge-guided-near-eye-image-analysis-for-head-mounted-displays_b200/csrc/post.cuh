@@ -403,6 +403,135 @@ ellipse_refine_kernel(const uint8_t* __restrict__ argmax, const float* __restric
 
 
 // ------------------------------------------------------------------------------------------
+// In-forward loss slot: models/RITnet_v2.py:372-440 get_allLoss with loss.py:48-137
+// (get_segLoss = alpha * SurfaceLoss + (1 - alpha) * GDiceLoss + wCE per sample with a GT mask,
+// get_ptLoss, get_seg2ptLoss).  Pass 1 reads logits / target / spatial weights / distance maps once
+// and leaves 14 partial sums per (frame, slice); pass 2 finishes the per-sample terms and the batch
+// reduction.  total = l_seg2pt + 20 * l_seg + 10 * (l_pt + l_ellipse).
+#define LOSS_SLICES 8
+#define LOSS_TERMS 14
+
+__global__ void __launch_bounds__(256) seg_loss_kernel(const float* __restrict__ logits,
+                                                       const uint8_t* __restrict__ label, int label_stride,
+                                                       const float* __restrict__ spat_w,
+                                                       const float* __restrict__ dist_map,
+                                                       double* __restrict__ partial /*[B][LOSS_SLICES][LOSS_TERMS]*/) {
+  const int slice = blockIdx.x, n = blockIdx.y;
+  const int HW = EGN_H * EGN_W;
+  const float* l0 = logits + (size_t)n * 3 * HW;
+  const float* d0 = dist_map + (size_t)n * 3 * HW;
+  const float* w0 = spat_w + (size_t)n * HW;
+  const uint8_t* t0 = label + (size_t)n * HW * label_stride;
+  float acc[LOSS_TERMS];
+#pragma unroll
+  for (int i = 0; i < LOSS_TERMS; ++i) acc[i] = 0.f;
+  const int per = HW / LOSS_SLICES;
+  for (int i = slice * per + threadIdx.x; i < (slice + 1) * per; i += 256) {
+    const float a = __ldg(l0 + i), b = __ldg(l0 + HW + i), c = __ldg(l0 + 2 * HW + i);
+    const float m = fmaxf(a, fmaxf(b, c));
+    const float ea = expf(a - m), eb = expf(b - m), ec = expf(c - m);
+    const float sum = ea + eb + ec, inv = 1.0f / sum;
+    const float p[3] = {ea * inv, eb * inv, ec * inv};
+    const int t = t0[(size_t)i * label_stride];
+    const float lt = t == 0 ? a : (t == 1 ? b : c);
+    acc[3] += logf(sum) - (lt - m);                   // -log softmax(target)
+    acc[4] += __ldg(w0 + i);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      acc[k] = fmaf(p[k], __ldg(d0 + (size_t)k * HW + i), acc[k]);
+      acc[5 + k] += (t == k) ? p[k] : 0.f;
+      acc[8 + k] += p[k];
+      acc[11 + k] += (t == k) ? 1.f : 0.f;
+    }
+  }
+  __shared__ double red[8][LOSS_TERMS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < LOSS_TERMS; ++k) {
+    double v = (double)acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < LOSS_TERMS) {
+    double v = 0;
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    partial[((size_t)n * LOSS_SLICES + slice) * LOSS_TERMS + threadIdx.x] = v;
+  }
+}
+
+// One block.  cond: [B][4] (cond[:,1] == 0 <=> the sample has a GT mask); pupil_c: [B][2] pixels;
+// el_norm: [B][2][5]; el_out / el_pred: [B][10]; loss: [1].
+__global__ void __launch_bounds__(256) seg_loss_finish_kernel(const double* __restrict__ partial,
+                                                              const float* __restrict__ cond,
+                                                              const float* __restrict__ pupil_c,
+                                                              const float* __restrict__ el_norm,
+                                                              const float* __restrict__ el_out,
+                                                              const float* __restrict__ el_pred, float alpha,
+                                                              float* __restrict__ loss, int B) {
+  const double HW = (double)(EGN_H * EGN_W);
+  // [0] sum seg loss over masked samples, [1] masked count, [2] sum |pupil seg centre - gt| (2 per sample),
+  // [3] sum |iris seg centre - gt| over masked, [4] sum l1(latent pupil centre) over unmasked, [5] sum l1(ellipse) over masked
+  double t[6] = {0, 0, 0, 0, 0, 0};
+  for (int n = threadIdx.x; n < B; n += blockDim.x) {
+    const bool mask = cond[n * 4 + 1] == 0.0f;          // loc_onlyMask = 1 - cond[:,1]
+    const float gx = 2.0f * (pupil_c[n * 2] / (float)EGN_W) - 1.0f;     // utils.normPts
+    const float gy = 2.0f * (pupil_c[n * 2 + 1] / (float)EGN_H) - 1.0f;
+    const float* eo = el_out + (size_t)n * 10;
+    const float* ep = el_pred + (size_t)n * 10;
+    const float* en = el_norm + (size_t)n * 10;
+    t[2] += (double)fabsf(ep[5] - gx) + (double)fabsf(ep[6] - gy);
+    if (mask) {
+      double s[LOSS_TERMS];
+      for (int k = 0; k < LOSS_TERMS; ++k) {
+        double v = 0;
+        for (int sl = 0; sl < LOSS_SLICES; ++sl) v += partial[((size_t)n * LOSS_SLICES + sl) * LOSS_TERMS + k];
+        s[k] = v;
+      }
+      const double l_sl = (s[0] / HW + s[1] / HW + s[2] / HW) / 3.0;            // loss.py:91-97
+      const double l_ce = (s[4] / HW) * (s[3] / HW);                             // loss.py:125-137
+      double A = 0, Bv = 0;                                                      // loss.py:99-123
+      for (int k = 0; k < 3; ++k) {
+        const double nk = s[11 + k];
+        const double w = nk > 0 ? 1.0 / fmax(nk * nk, 1e-5) : 0.0;
+        A += w * s[5 + k];
+        Bv += w * (s[8 + k] + nk);
+      }
+      const double dice = 2.0 * A / Bv;
+      const double l_gd = 1.0 - fmax(dice, 1e-5);
+      t[0] += (double)alpha * l_sl + (1.0 - (double)alpha) * l_gd + l_ce;
+      t[1] += 1.0;
+      t[3] += (double)fabsf(ep[0] - en[0]) + (double)fabsf(ep[1] - en[1]);
+      double e10 = 0;
+      for (int k = 0; k < 10; ++k) e10 += (double)fabsf(eo[k] - en[k]);
+      t[5] += e10 / 10.0;
+    } else {
+      t[4] += ((double)fabsf(eo[5] - gx) + (double)fabsf(eo[6] - gy)) / 2.0;
+    }
+  }
+  __shared__ double red[8][6];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = 0; k < 6; ++k) {
+    double v = t[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r[6] = {0, 0, 0, 0, 0, 0};
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
+      for (int k = 0; k < 6; ++k) r[k] += red[w][k];
+    const double nm = r[1], nu = (double)B - nm;
+    const double l_seg = nm > 0 ? r[0] / nm : 0.0;
+    const double l_pup = r[2] / (2.0 * B);
+    const double l_iri = nm > 0 ? r[3] / (2.0 * nm) : 0.0;
+    const double l_pt = nu > 0 ? r[4] / nu : 0.0;
+    const double l_el = nm > 0 ? r[5] / nm : 0.0;
+    loss[0] = (float)(0.5 * l_pup + 0.5 * l_iri + 20.0 * l_seg + 10.0 * (l_pt + l_el));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Ingest: per-frame z-score of uint8 frames, (img - mean) / std with numpy's
 // population std evaluated in float64 and the result cast to float32 (evaluate.py:102-103,
 // CurriculumLib.py:139-140).  One block per frame: exact integer sum / sum of squares, then the

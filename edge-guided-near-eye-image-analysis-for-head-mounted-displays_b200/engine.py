@@ -103,6 +103,22 @@ class Context:
                                                    _ptr(cond), _ptr(pc), _ptr(ic), _ptr(el_out), _ptr(el_pred), _ptr(acc),
                                                    _ptr(iou_by_sample), B, _stream(self.device)))
 
+    def forward_loss(self, logits, target, spat_w, dist_map, cond, pupil_c, el_norm, el_out, el_pred, alpha=0.0):
+        """get_allLoss (models/RITnet_v2.py:372-440) forward value: fp32 tensor [1] on the device."""
+        B = int(logits.shape[0])
+        tgt = target.to(self.device)
+        if tgt.dtype not in (torch.uint8, torch.int64):
+            tgt = tgt.to(torch.int64)
+        tgt = tgt.contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=self.device)
+        sw, dm, cd = _f32c(spat_w, self.device), _f32c(dist_map, self.device), _f32c(cond, self.device)
+        pc, en = _f32c(pupil_c, self.device), _f32c(el_norm.reshape(B, 10), self.device)
+        assert tuple(sw.shape) == (B, H, W) and tuple(dm.shape) == (B, 3, H, W) and tuple(tgt.shape) == (B, H, W)
+        _lib.check(self.lib.egn_forward_loss(self.h, _ptr(logits), _ptr(tgt), int(tgt.dtype == torch.int64), _ptr(sw),
+                                             _ptr(dm), _ptr(cd), _ptr(pc), _ptr(en), _ptr(el_out), _ptr(el_pred),
+                                             ctypes.c_float(float(alpha)), _ptr(loss), B, _stream(self.device)))
+        return loss
+
     def ellipse_refine(self, argmax, ell_norm, refine=True):
         B = int(argmax.shape[0])
         ell = _f32c(ell_norm.reshape(B, 2, 5), self.device)

@@ -2,8 +2,9 @@
 
 Same constructor (yaml ``setting`` dict), state_dict key set, ``.to()/.cuda()/.eval()`` and
 ``__call__`` signature / 5-tuple return; the forward runs in libegn.so.  Always evaluates with the
-BatchNorm running statistics (what test.py:49 does).  The training-loss slot of the reference's
-forward (RITnet_v2.py:312-323, loss.py) is out of scope and returned as zeros(1)."""
+BatchNorm running statistics (what test.py:49 does).  The loss slot of the reference's forward
+(get_allLoss, RITnet_v2.py:312-323,372-440) is evaluated on the device (forward value, no autograd)
+when the caller passes the target tensors, and is zeros(1) when they are None."""
 import torch
 
 from ._modules import EngineBound
@@ -54,5 +55,11 @@ class DenseNet2D(EngineBound):
                 cond=None, ID=None, alpha=0):
         logits, el_out, latent, argmax, el_pred = self.infer(x, x_edge, cond)
         self.last_argmax = argmax            # u8 [B,H,W] on device, reused by egn_b200.get_predictions
-        loss = torch.zeros(1, dtype=torch.float32, device=x.device)
+        tensors = (target, pupil_center, elNorm, spatWts, distMap, cond)
+        if all(torch.is_tensor(t) for t in tensors):
+            # the loss slot of the reference forward (RITnet_v2.py:312-323): forward value only
+            loss = self._ensure_ctx(x.device).forward_loss(logits, target, spatWts, distMap, cond, pupil_center, elNorm,
+                                                           el_out, el_pred, alpha)
+        else:
+            loss = torch.zeros(1, dtype=torch.float32, device=x.device)
         return logits, el_pred, latent, loss, el_out

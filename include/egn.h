@@ -78,6 +78,17 @@ int egn_metrics_accumulate(egn_ctx* ctx, const uint8_t* argmax_u8, const void* l
                            const float* el_out, const float* el_pred, double* acc,
                            float* iou_by_sample, int batch, void* stream);
 
+/* Replaces: the loss slot of DenseNet2D.forward, get_allLoss (models/RITnet_v2.py:312-323,372-440) with
+ * loss.get_segLoss / SurfaceLoss / GDiceLoss / wCE / get_ptLoss / get_seg2ptLoss (loss.py:16-137):
+ * total = l_seg2pt + 20 * l_seg + 10 * (l_pt + l_ellipse), forward value only (no gradients).
+ * target: [B,240,320] u8 or int64; spat_w: [B,240,320]; dist_map: [B,3,240,320]; cond: [B,4];
+ * pupil_c: [B,2] pixels; el_norm: [B,2,5]; el_out, el_pred: [B,10] (el_pred from egn_seg_post);
+ * loss: [1] fp32.  Samples whose GT lacks more than one class make the reference raise
+ * (loss.py:128-132); here their cross-entropy is simply taken over all pixels. */
+int egn_forward_loss(egn_ctx* ctx, const float* logits, const void* target, int target_is_i64, const float* spat_w,
+                     const float* dist_map, const float* cond, const float* pupil_c, const float* el_norm,
+                     const float* el_out, const float* el_pred, float alpha, float* loss, int batch, void* stream);
+
 /* Replaces: my_ellipse(norm).transform(H) + search_proper_parameter_iou_for_our_data
  * (evaluate.py:141-151, helperfunctions.py:25-63,102-129, utils.py:176-204,450-486).
  * ell_norm: [B,2,5] normalised ellipses (iris, pupil) = elPred; out: [B,2,5] fp64 pixel-space

@@ -269,6 +269,75 @@ def get_predictions(op):
     return op.max(1)[1]
 
 
+# ----------------------------------------------------------------------------- loss slot
+
+def norm_pts(pts, sz):
+    """utils.py:627-634 normPts: pixel (x, y) -> [-1, 1] with x / W, y / H."""
+    p = torch.as_tensor(pts, dtype=torch.float32).clone().reshape(-1, 2)
+    p[:, 0] = 2 * (p[:, 0] / sz[1]) - 1
+    p[:, 1] = 2 * (p[:, 1] / sz[0]) - 1
+    return p
+
+
+def surface_loss(op_i, dist_i):
+    """loss.py:91-97 SurfaceLoss for one sample: mean over channels of the pixel mean of
+    softmax(op) * distmap."""
+    p = torch.softmax(op_i, 0).flatten(1)
+    return (p * dist_i.flatten(1)).mean(1).mean()
+
+
+def wce_loss(op_i, target_i, spat_i):
+    """loss.py:125-137 wCE: mean(spatWts * cross_entropy(...)) where cross_entropy is the scalar
+    mean over pixels (ignore_index is the single class absent from the target, which no pixel
+    carries, so nothing is ignored)."""
+    ce = F.cross_entropy(op_i.flatten(1).unsqueeze(0), target_i.flatten().unsqueeze(0).long())
+    return (spat_i.flatten() * ce).mean()
+
+
+def gdice_loss(op_i, target_i):
+    """loss.py:99-123 GDiceLoss for one sample: class weights 1 / clamp(count^2, 1e-5), zero for
+    classes absent from the target; 1 - clamp(2 * sum(w * p.t) / sum(w * (p + t)), 1e-5)."""
+    C = op_i.shape[0]
+    p = torch.softmax(op_i, 0).flatten(1)
+    t = torch.stack([(target_i.flatten() == c).to(p.dtype) for c in range(C)])
+    cnt = t.sum(1)
+    w = 1.0 / (cnt ** 2).clamp(1e-5)
+    w = torch.where(cnt > 0, w, torch.zeros_like(w))
+    dice = 2.0 * (w * (p * t).sum(1)).sum() / (w * (p + t).sum(1)).sum()
+    return 1 - dice.clamp(1e-5)
+
+
+def all_loss(op, el_out, target, pupil_center, el_norm, spat_w, dist_map, cond, alpha):
+    """models/RITnet_v2.py:372-440 get_allLoss (with loss.py:48-89 get_segLoss / get_ptLoss):
+    returns (total_loss scalar, pred_c_seg [B,2,2] iris first)."""
+    B, C, H, W = op.shape
+    mask = (1 - cond[:, 1]).to(torch.float32)
+    gt_pup = norm_pts(pupil_center, (H, W))
+    pup = seg2pt_exact(op[:, 2])
+    l_pup = (pup - gt_pup).abs()
+    if mask.sum() > 0:
+        iri = seg2pt_exact(-op[:, 0])
+        l_iri = (iri - el_norm[:, 0, :2]).abs()
+        tmp = torch.stack([mask, mask], 1)
+        l_iri = (l_iri * tmp).sum() / tmp.sum()
+    else:
+        l_iri = 0.0
+        iri = el_out[:, 5:7].clone()
+    l_seg2pt = 0.5 * l_pup.mean() + 0.5 * l_iri
+    seg = [alpha * surface_loss(op[i], dist_map[i]) + (1 - alpha) * gdice_loss(op[i], target[i]) +
+           wce_loss(op[i], target[i], spat_w[i]) for i in range(B) if mask[i] == 1]
+    l_seg = torch.stack(seg).sum() / mask.sum() if seg else 0.0
+
+    def pt_loss(a, b, c):
+        v = [(a[i] - b[i]).abs().mean() for i in range(B) if c[i] == 1]
+        return torch.stack(v).sum() / c.sum() if v else 0.0
+
+    l_pt = pt_loss(el_out[:, 5:7], gt_pup, 1 - mask)
+    l_el = pt_loss(el_out, el_norm.reshape(-1, 10), mask)
+    total = l_seg2pt + 20 * l_seg + 10 * (l_pt + l_el)
+    return torch.as_tensor(total, dtype=torch.float32), torch.stack([iri, pup], 1)
+
+
 # ----------------------------------------------------------------------------- metrics
 
 def seg_metrics(y_true, y_pred, cond):

@@ -23,6 +23,7 @@ import math
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 H, W = 240, 320
 
@@ -303,3 +304,27 @@ def evaluate_style_labels(b):
     lab[:, 0, 2] = 1
     lab[:, 2, 2] = 2
     return lab
+
+
+def _blur(x, k=9):
+    """Box blur of a [B,C,H,W] float tensor (deterministic helper for the synthetic loss inputs)."""
+    return F.avg_pool2d(x, k, 1, k // 2, count_include_pad=True)
+
+
+def smooth_logits(label, seed=0):
+    """Plausible segmentation logits [B,3,H,W] for labels [B,H,W]: 4 * one-hot + smooth noise, so the
+    softmax is neither saturated nor uniform (inputs of the loss-slot fixtures, tests/golden/loss.npz)."""
+    lab = torch.as_tensor(np.asarray(label)).long()
+    g = torch.Generator().manual_seed(seed)
+    onehot = F.one_hot(lab, 3).permute(0, 3, 1, 2).float()
+    return 4.0 * onehot + 2.0 * _blur(torch.randn(onehot.shape, generator=g)) + 0.3 * torch.randn(onehot.shape, generator=g)
+
+
+def loss_maps(label, seed=0):
+    """Synthetic spatial weights [B,H,W] (>= 1) and signed distance-like maps [B,3,H,W] for the loss slot."""
+    lab = torch.as_tensor(np.asarray(label))
+    g = torch.Generator().manual_seed(seed)
+    B = lab.shape[0]
+    sw = 1.0 + 6.0 * _blur(torch.randn((B, 1, H, W), generator=g)).abs()[:, 0]
+    dm = 20.0 * _blur(torch.randn((B, 3, H, W), generator=g), 15)
+    return sw, dm

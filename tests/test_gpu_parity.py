@@ -349,3 +349,38 @@ def test_calc_acc_mirror_on_synthetic_loader(env, capsys):
     for got, want in zip(out[1:], (dpl, dil, dps, dis)):
         assert abs(got - np.nanmean(want)) < 0.25                            # centres within 0.25 px
     assert len(by) == 2 and by[0].shape == (3, 3) and by[1].shape == (2, 3)
+
+
+def test_forward_loss_slot(env):
+    """The loss slot of DenseNet2D.forward (get_allLoss, RITnet_v2.py:312-323,372-440) on the device:
+    (1) egn_forward_loss on the fixture's inputs against the reference's own totals, for both label
+    dtypes and for a batch without masks; (2) through the module call, against the oracle's loss on
+    the oracle's forward outputs."""
+    egn, g, synth, dev = env["egn"], env["graph"], env["synth"], env["dev"]
+    gold = np.load(os.path.join(env["golden"], "loss.npz"))
+    eb = synth.synthetic_eye_batch(500, 4)
+    cond = torch.from_numpy(eb["cond"]).clone().float(); cond[2, 1] = 1
+    op = synth.smooth_logits(eb["label"], seed=5)
+    sw, dm = synth.loss_maps(eb["label"], seed=6)
+    tgt, pc, en = torch.from_numpy(eb["label"]), torch.from_numpy(eb["pupil_center"]).float(), torch.from_numpy(eb["elNorm"]).float()
+    el_out = torch.from_numpy(gold["el_out"])
+    ctx = env["edge_model"].context(dev)
+    for cnd, keys in ((cond, (("total_a0", 0.0), ("total_a5", 0.5), ("total_a10", 1.0))),
+                      (torch.tensor([[0, 1, 0, 0]] * 4).float(), (("total_nomask", 0.5),))):
+        am, el_pred = ctx.seg_post(op.to(dev).contiguous(), el_out.to(dev), cnd.to(dev))
+        for key, alpha in keys:
+            for lab in (tgt.to(torch.uint8), tgt.to(torch.int64)):
+                loss = ctx.forward_loss(op.to(dev).contiguous(), lab, sw, dm, cnd, pc, en, el_out.to(dev), el_pred, alpha)
+                assert loss.shape == (1,)
+                assert float(loss.item()) == pytest.approx(float(gold[key]), rel=2e-4), (key, lab.dtype)
+    # through the module: the 4th output of the reference's 5-tuple
+    m, st, esd = _model(env, "baseline_edge")
+    x = torch.from_numpy(eb["img"])
+    with torch.no_grad():
+        e_ref = g.calc_edge(env["bsd"], x)
+        ref = g.esf_forward(esd, st, x, e_ref)
+        want, _ = g.all_loss(ref["op"], ref["elOut"], tgt.long(), pc, en, sw, dm, cond, 0.5)
+        out = m(x.to(dev), e_ref.to(dev), tgt.long().to(dev), pc.to(dev), en.to(dev), sw.to(dev), dm.to(dev),
+                cond.to(dev), torch.zeros(4, dtype=torch.long, device=dev), 0.5)
+    assert out[3].shape == (1,) and out[3].is_cuda
+    assert float(out[3].item()) == pytest.approx(float(want), rel=5e-3)

@@ -82,3 +82,35 @@ def test_metrics(golden_dir):
     pd, pds = graph.point_metric(g["ptrue"], g["ppred"], g["cond"], (240, 320))
     assert pd == pytest.approx(float(g["pd"]), rel=1e-6)
     np.testing.assert_allclose(pds, g["pds"], rtol=1e-5, atol=1e-5)
+
+
+def _loss_inputs():
+    from oracle import synth
+    eb = synth.synthetic_eye_batch(500, 4)
+    cond = torch.from_numpy(eb["cond"]).clone().float()
+    cond[2, 1] = 1
+    op = synth.smooth_logits(eb["label"], seed=5)
+    sw, dm = synth.loss_maps(eb["label"], seed=6)
+    return dict(op=op, tgt=torch.from_numpy(eb["label"]).long(), pc=torch.from_numpy(eb["pupil_center"]).float(),
+                en=torch.from_numpy(eb["elNorm"]).float(), sw=sw, dm=dm, cond=cond)
+
+
+def test_loss_slot_against_reference_fixture(golden_dir):
+    """get_allLoss and its per-sample terms (models/RITnet_v2.py:372-440, loss.py:48-137): the oracle
+    on regenerated seeded inputs against the values the real reference produced (oracle/make_golden_loss.py)."""
+    from oracle import graph
+    g = np.load(os.path.join(golden_dir, "loss.npz"))
+    d = _loss_inputs()
+    el_out = torch.from_numpy(g["el_out"])
+    for key, alpha in (("total_a0", 0.0), ("total_a5", 0.5), ("total_a10", 1.0)):
+        total, pcs = graph.all_loss(d["op"], el_out, d["tgt"], d["pc"], d["en"], d["sw"], d["dm"], d["cond"], alpha)
+        assert float(total) == pytest.approx(float(g[key]), rel=1e-5)
+        assert pcs.shape == (4, 2, 2)
+    cn = d["cond"].clone(); cn[:, 1] = 1
+    total, pcs = graph.all_loss(d["op"], el_out, d["tgt"], d["pc"], d["en"], d["sw"], d["dm"], cn, 0.5)
+    assert float(total) == pytest.approx(float(g["total_nomask"]), rel=1e-5)
+    np.testing.assert_allclose(pcs[:, 0].numpy(), el_out[:, 5:7].numpy())       # iris centre := elOut[:,5:7]
+    for i in range(4):
+        assert float(graph.surface_loss(d["op"][i], d["dm"][i])) == pytest.approx(float(g["surface"][i]), rel=1e-4, abs=1e-7)
+        assert float(graph.wce_loss(d["op"][i], d["tgt"][i], d["sw"][i])) == pytest.approx(float(g["wce"][i]), rel=1e-5)
+        assert float(graph.gdice_loss(d["op"][i], d["tgt"][i])) == pytest.approx(float(g["gdice"][i]), rel=1e-5)
