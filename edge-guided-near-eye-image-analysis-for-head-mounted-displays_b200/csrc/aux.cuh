@@ -108,77 +108,6 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p
 }
 
 // ------------------------------------------------------------------------------------------
-// Last layer: dec.final.conv2 32->3 3x3 + leaky-relu + eval BatchNorm -> fp32 NCHW logits
-// (utils.py:1046-1050).  A 16x16-pixel block stages its 18x18x32 input window in shared memory as
-// fp32 (one split-bf16 -> fp32 conversion per input value instead of nine); one thread per pixel.
-// The 864 weights travel in the kernel parameters and are read through the constant bank.
-struct LastConvParams {
-  View src;             // 32 channels
-  float w[9 * 32 * 3];  // [tap][cin][3]
-  float bias[3];
-  float scale[3];       // BN folded: y = act(conv)*scale + shift
-  float shift[3];
-  float* out;           // [B][3][H][W]
-  int B, H, W;
-};
-
-#define LAST_TILE 16
-#define LAST_PITCH 36   // floats per staged pixel: 32 channels + 4 pad -> conflict-free 128-bit reads
-
-__global__ void __launch_bounds__(256) last_conv_kernel(const __grid_constant__ LastConvParams p) {
-  __shared__ __align__(16) float tile[(LAST_TILE + 2) * (LAST_TILE + 2) * LAST_PITCH];
-  const int n = blockIdx.z;
-  const int y0 = blockIdx.y * LAST_TILE, x0 = blockIdx.x * LAST_TILE;
-  constexpr int TW = LAST_TILE + 2;
-  for (int i = threadIdx.x; i < TW * TW * 4; i += 256) {
-    const int g = i & 3, pix = i >> 2;
-    const int ty = pix / TW, tx = pix % TW;
-    const int yy = y0 + ty - 1, xx = x0 + tx - 1;
-    float v[8];
-    if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
-      load8(p.src.hi, p.src.lo, ((size_t)(n + p.src.n_off) * p.H * p.W + (size_t)yy * p.W + xx) * p.src.C + p.src.coff + g * 8, v);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = 0.f;
-    }
-    float4* d = reinterpret_cast<float4*>(tile + pix * LAST_PITCH + g * 8);
-    d[0] = make_float4(v[0], v[1], v[2], v[3]);
-    d[1] = make_float4(v[4], v[5], v[6], v[7]);
-  }
-  __syncthreads();
-  const int ty = threadIdx.x / LAST_TILE, tx = threadIdx.x % LAST_TILE;
-  const int y = y0 + ty, x = x0 + tx;
-  float a0 = p.bias[0], a1 = p.bias[1], a2 = p.bias[2];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-#pragma unroll
-    for (int s2 = 0; s2 < 3; ++s2) {
-      const float4* src = reinterpret_cast<const float4*>(tile + ((ty + r) * TW + tx + s2) * LAST_PITCH);
-      const float* w = p.w + (r * 3 + s2) * 96;
-#pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 v = src[c4];
-        const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = c4 * 4 + k;
-          a0 = fmaf(vv[k], w[c * 3 + 0], a0);
-          a1 = fmaf(vv[k], w[c * 3 + 1], a1);
-          a2 = fmaf(vv[k], w[c * 3 + 2], a2);
-        }
-      }
-    }
-  }
-  if (y < p.H && x < p.W) {
-    const size_t hw = (size_t)p.H * p.W;
-    const size_t o = (size_t)n * 3 * hw + (size_t)y * p.W + x;
-    p.out[o] = apply_act(a0, ACT_LRELU) * p.scale[0] + p.shift[0];
-    p.out[o + hw] = apply_act(a1, ACT_LRELU) * p.scale[1] + p.shift[1];
-    p.out[o + 2 * hw] = apply_act(a2, ACT_LRELU) * p.scale[2] + p.shift[2];
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // MaxPool2d(2, stride s, ceil_mode=True) (vgg16_c.py:15,20,27,34).  Copies the winning hi/lo pair.
 struct PoolParams {
   View src, dst;

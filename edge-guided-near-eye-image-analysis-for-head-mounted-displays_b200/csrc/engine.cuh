@@ -170,7 +170,6 @@ struct Engine {
     ConvLayer head2, final1, final2;
     Block blk[5];
     UpBlock up[4];
-    LastConvParams last;
     // regression head + AdaIN (fp32)
     int Cf = 0;
     Act *hin, *c1o;               // AdaIN-transformed head input (add_seg only); lrelu(c1(x))
@@ -786,7 +785,7 @@ struct Engine {
       set_store_epilogue(u.c22, u.out, 0, ACT_LRELU);
       finalize_conv(u.c22);
     }
-    // final convBlock: conv1 (TC) -> fin ; conv2 + lrelu + BN -> fp32 NCHW logits (SIMT)
+    // final convBlock: conv1 -> fin ; conv2 + lrelu + BN -> fp32 NCHW logits (both on the tensor cores)
     es.fin = new_act(mem, mb, 240, 320, 32);
     debug_acts["dec.final.conv1"] = {es.fin, {0, 32}};
     {
@@ -798,10 +797,6 @@ struct Engine {
       finalize_conv(es.final1);
       const HostTensor& w2 = sd_get(sd, "dec.final.conv2.weight");     // [3][32][3][3]
       const HostTensor& b2 = sd_get(sd, "dec.final.conv2.bias");
-      std::vector<float> wp(9 * 32 * 3);
-      for (int co = 0; co < 3; ++co)
-        for (int c = 0; c < 32; ++c)
-          for (int t = 0; t < 9; ++t) wp[((size_t)t * 32 + c) * 3 + co] = w2.data[((size_t)co * 32 + c) * 9 + t];
       {
         // conv2 (32 -> 3) + lrelu + BN on the tensor cores too: N = 16 tile (3 live columns), fp32 NCHW logits
         build_conv(es.final2, mem, "dec.final.conv2", {{es.fin, 0, 32, 0}}, {{w2.data.data(), b2.data.data(), 1, 1}}, 3, 32,
@@ -814,12 +809,6 @@ struct Engine {
         e.logits = nullptr; e.logits_c = 3;
         finalize_conv(es.final2);
       }
-      std::vector<float> shift;
-      std::vector<float> scale = bn_scale(sd, "dec.final.bn", 3, 3, shift);
-      es.last.src = make_view(*es.fin, 0);
-      for (int i = 0; i < 9 * 32 * 3; ++i) es.last.w[i] = wp[i];
-      for (int i = 0; i < 3; ++i) { es.last.bias[i] = b2.data[i]; es.last.scale[i] = scale[i]; es.last.shift[i] = shift[i]; }
-      es.last.H = 240; es.last.W = 320;
     }
     // regression head (utils.py:983-1037), fp32
     const int Cf = 153 * (cfg.add_edge ? 2 : 1);
@@ -1013,23 +1002,14 @@ struct Engine {
         run_conv(u.c22, nb, st);
       }
       run_conv(es.final1, nb, st);
-      LastConvParams lp = es.last;
-      lp.B = nb; lp.out = logits + (size_t)b0 * 3 * hw;
-      static const bool last_simt = getenv("EGN_LAST_SIMT") != nullptr;     // tuning knob: the fp32 CUDA-core kernel
-      if (last_simt) {
-        aux("esf.last_conv", st, [&] {
-          last_conv_kernel<<<dim3(EGN_W / LAST_TILE, EGN_H / LAST_TILE, nb), 256, 0, st>>>(lp);
-          CUDA_OK(cudaGetLastError()); ++launches;
-        });
-      } else {
-        es.final2.tc.e.logits = lp.out; es.final2.simt.e.logits = lp.out;
-        run_conv(es.final2, nb, st);
-      }
+      float* lg = logits + (size_t)b0 * 3 * hw;
+      es.final2.tc.e.logits = lg; es.final2.simt.e.logits = lg;
+      run_conv(es.final2, nb, st);
       // ---- AdaIN parameters from the softmaxed segmentation (RITnet_v2.py:289-308)
       if (cfg.add_seg) {
         {
           const long long total = (long long)nb * hw;
-          softmax3_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(lp.out, es.sm, nb, (int)hw);
+          softmax3_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(lg, es.sm, nb, (int)hw);
           CUDA_OK(cudaGetLastError()); ++launches;
         }
         {
