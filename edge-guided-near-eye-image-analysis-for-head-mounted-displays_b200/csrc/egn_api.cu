@@ -202,7 +202,7 @@ int egn_preprocess_u8(egn_ctx* ctx, const uint8_t* frames_u8, float* out, int ba
   API_BEGIN
   EGN_CHECK(ctx && frames_u8 && out && batch > 0, "bad argument");
   CUDA_OK(cudaSetDevice(ctx->eng.device));
-  preprocess_u8_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(frames_u8, out);
+  preprocess_u8_kernel<<<batch, PRE_THREADS, 0, (cudaStream_t)stream>>>(frames_u8, out);
   CUDA_OK(cudaGetLastError());
   ctx->eng.launches += 1;
   API_END

@@ -134,19 +134,39 @@ __global__ void seg_post_finish_kernel(const float* __restrict__ partial, const 
 
 // ------------------------------------------------------------------------------------------
 // K7: per-frame class counts (utils.py:120-150).  label_stride: 1 (u8) or 8 (int64 little endian).
+// 128-bit loads; the nine counters (per class: GT, prediction, intersection) come from byte-wise SIMD
+// compares (__vcmpeq4) and popcounts of four pixels at a time.
+__device__ __forceinline__ uint32_t low_bytes4(const uint4 a, const uint4 b) {   // four int64 labels -> four bytes
+  return (a.x & 0xffu) | ((a.z & 0xffu) << 8) | ((b.x & 0xffu) << 16) | ((b.z & 0xffu) << 24);
+}
+
+__device__ __forceinline__ void count4(uint32_t p, uint32_t t, int c[9]) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const uint32_t pat = 0x01010101u * (uint32_t)k;
+    const uint32_t et = __vcmpeq4(t, pat), ep = __vcmpeq4(p, pat);
+    c[k] += __popc(et) >> 3; c[3 + k] += __popc(ep) >> 3; c[6 + k] += __popc(et & ep) >> 3;
+  }
+}
+
 __global__ void __launch_bounds__(256) seg_counts_kernel(const uint8_t* __restrict__ pred,
                                                          const uint8_t* __restrict__ label, int label_stride,
                                                          int* __restrict__ counts /*[B][9]*/, int HW) {
   const int n = blockIdx.y;
   int c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};     // t0 t1 t2 p0 p1 p2 i0 i1 i2
-  const uint8_t* pp = pred + (size_t)n * HW;
-  const uint8_t* ll = label + (size_t)n * HW * label_stride;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-    const int p = pp[i], t = ll[(size_t)i * label_stride];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      c[k] += (t == k); c[3 + k] += (p == k); c[6 + k] += (t == k && p == k);
+  const uint4* pp = reinterpret_cast<const uint4*>(pred + (size_t)n * HW);
+  const uint4* ll = reinterpret_cast<const uint4*>(label + (size_t)n * HW * label_stride);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW / 16; i += gridDim.x * blockDim.x) {
+    const uint4 p = __ldg(pp + i);
+    uint4 t;
+    if (label_stride == 1) {
+      t = __ldg(ll + i);
+    } else {
+      const uint4* l8 = ll + (size_t)i * 8;       // 16 int64 labels = 8 x 16 bytes
+      t.x = low_bytes4(__ldg(l8 + 0), __ldg(l8 + 1)); t.y = low_bytes4(__ldg(l8 + 2), __ldg(l8 + 3));
+      t.z = low_bytes4(__ldg(l8 + 4), __ldg(l8 + 5)); t.w = low_bytes4(__ldg(l8 + 6), __ldg(l8 + 7));
     }
+    count4(p.x, t.x, c); count4(p.y, t.y, c); count4(p.z, t.z, c); count4(p.w, t.w, c);
   }
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
@@ -425,23 +445,41 @@ __global__ void __launch_bounds__(256) seg_loss_kernel(const float* __restrict__
   float acc[LOSS_TERMS];
 #pragma unroll
   for (int i = 0; i < LOSS_TERMS; ++i) acc[i] = 0.f;
-  const int per = HW / LOSS_SLICES;
-  for (int i = slice * per + threadIdx.x; i < (slice + 1) * per; i += 256) {
-    const float a = __ldg(l0 + i), b = __ldg(l0 + HW + i), c = __ldg(l0 + 2 * HW + i);
-    const float m = fmaxf(a, fmaxf(b, c));
-    const float ea = expf(a - m), eb = expf(b - m), ec = expf(c - m);
-    const float sum = ea + eb + ec, inv = 1.0f / sum;
-    const float p[3] = {ea * inv, eb * inv, ec * inv};
-    const int t = t0[(size_t)i * label_stride];
-    const float lt = t == 0 ? a : (t == 1 ? b : c);
-    acc[3] += logf(sum) - (lt - m);                   // -log softmax(target)
-    acc[4] += __ldg(w0 + i);
+  const int per4 = HW / LOSS_SLICES / 4;               // float4 groups per slice
+  const float4* l4 = reinterpret_cast<const float4*>(l0);
+  const float4* d4 = reinterpret_cast<const float4*>(d0);
+  const float4* w4 = reinterpret_cast<const float4*>(w0);
+  for (int q = slice * per4 + threadIdx.x; q < (slice + 1) * per4; q += 256) {
+    const float4 A = __ldg(l4 + q), Bq = __ldg(l4 + HW / 4 + q), C = __ldg(l4 + HW / 2 + q);
+    const float4 D0 = __ldg(d4 + q), D1 = __ldg(d4 + HW / 4 + q), D2 = __ldg(d4 + HW / 2 + q);
+    const float4 Wq = __ldg(w4 + q);
+    uint32_t tt;
+    if (label_stride == 1) {
+      tt = __ldg(reinterpret_cast<const uint32_t*>(t0) + q);
+    } else {
+      const uint4* l8 = reinterpret_cast<const uint4*>(t0) + (size_t)q * 2;
+      tt = low_bytes4(__ldg(l8), __ldg(l8 + 1));
+    }
+    const float av[4] = {A.x, A.y, A.z, A.w}, bv[4] = {Bq.x, Bq.y, Bq.z, Bq.w}, cv[4] = {C.x, C.y, C.z, C.w};
+    const float dv[3][4] = {{D0.x, D0.y, D0.z, D0.w}, {D1.x, D1.y, D1.z, D1.w}, {D2.x, D2.y, D2.z, D2.w}};
+    acc[4] += (Wq.x + Wq.y) + (Wq.z + Wq.w);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      acc[k] = fmaf(p[k], __ldg(d0 + (size_t)k * HW + i), acc[k]);
-      acc[5 + k] += (t == k) ? p[k] : 0.f;
-      acc[8 + k] += p[k];
-      acc[11 + k] += (t == k) ? 1.f : 0.f;
+    for (int j = 0; j < 4; ++j) {
+      const float a = av[j], b = bv[j], c = cv[j];
+      const float m = fmaxf(a, fmaxf(b, c));
+      const float ea = expf(a - m), eb = expf(b - m), ec = expf(c - m);
+      const float sum = ea + eb + ec, inv = 1.0f / sum;
+      const float p[3] = {ea * inv, eb * inv, ec * inv};
+      const int t = (tt >> (8 * j)) & 0xff;
+      const float lt = t == 0 ? a : (t == 1 ? b : c);
+      acc[3] += logf(sum) - (lt - m);                   // -log softmax(target)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        acc[k] = fmaf(p[k], dv[k][j], acc[k]);
+        acc[5 + k] += (t == k) ? p[k] : 0.f;
+        acc[8 + k] += p[k];
+        acc[11 + k] += (t == k) ? 1.f : 0.f;
+      }
     }
   }
   __shared__ double red[8][LOSS_TERMS];
@@ -536,47 +574,55 @@ __global__ void __launch_bounds__(256) seg_loss_finish_kernel(const double* __re
 // population std evaluated in float64 and the result cast to float32 (evaluate.py:102-103,
 // CurriculumLib.py:139-140).  One block per frame: exact integer sum / sum of squares, then the
 // normalised fp32 frame is written with 128-bit stores.
-__global__ void __launch_bounds__(256) preprocess_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ out) {
+#define PRE_THREADS 1024
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ out) {
   const int n = blockIdx.x;
   const int HW = EGN_H * EGN_W;
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(in + (size_t)n * HW);
-  unsigned long long s = 0, q = 0;
-  for (int i = threadIdx.x; i < HW / 4; i += 256) {
-    const uint32_t w = __ldg(src + i);
+  const uint4* src = reinterpret_cast<const uint4*>(in + (size_t)n * HW);
+  unsigned int s = 0, q = 0;                    // per thread: <= 80 bytes -> no overflow
+  for (int i = threadIdx.x; i < HW / 16; i += PRE_THREADS) {
+    const uint4 w = __ldg(src + i);
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const unsigned v = (w >> (8 * k)) & 0xffu;
-      s += v; q += v * v;
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned v = (ws[j] >> (8 * k)) & 0xffu;
+        s += v; q += v * v;
+      }
     }
   }
+  unsigned long long S = s, Q = q;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    q += __shfl_xor_sync(0xffffffffu, q, o);
+    S += __shfl_xor_sync(0xffffffffu, S, o);
+    Q += __shfl_xor_sync(0xffffffffu, Q, o);
   }
-  __shared__ unsigned long long ss[8], sq[8];
+  __shared__ unsigned long long ss[PRE_THREADS / 32], sq[PRE_THREADS / 32];
   __shared__ double sh_mean, sh_std;
-  if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = s; sq[threadIdx.x >> 5] = q; }
+  if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = S; sq[threadIdx.x >> 5] = Q; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    unsigned long long S = 0, Q = 0;
-    for (int w = 0; w < 8; ++w) { S += ss[w]; Q += sq[w]; }
-    const double mean = (double)S / HW;
+    unsigned long long St = 0, Qt = 0;
+    for (int w = 0; w < PRE_THREADS / 32; ++w) { St += ss[w]; Qt += sq[w]; }
+    const double mean = (double)St / HW;
     // sum (x - mean)^2 = Q - S^2 / N, exact in integers up to the final division
-    const double var = ((double)Q - (double)S * (double)S / HW) / HW;
+    const double var = ((double)Qt - (double)St * (double)St / HW) / HW;
     sh_mean = mean;
     sh_std = sqrt(var > 0.0 ? var : 0.0);
   }
   __syncthreads();
   const double mean = sh_mean, sd = sh_std;
+  // a uint8 pixel has 256 possible outputs: thread v builds entry v once (float64 divide like numpy)
+  __shared__ float lut[256];
+  if (threadIdx.x < 256) lut[threadIdx.x] = (float)(((double)threadIdx.x - mean) / sd);
+  __syncthreads();
   float4* dst = reinterpret_cast<float4*>(out + (size_t)n * HW);
-  for (int i = threadIdx.x; i < HW / 4; i += 256) {
-    const uint32_t w = __ldg(src + i);
+  const uint32_t* src4 = reinterpret_cast<const uint32_t*>(src);
+  for (int i = threadIdx.x; i < HW / 4; i += PRE_THREADS) {     // consecutive threads -> consecutive 16-byte stores
+    const uint32_t w = __ldg(src4 + i);             // second read: L1 / L2 hit
     float4 o;
-    o.x = (float)(((double)(w & 0xffu) - mean) / sd);
-    o.y = (float)(((double)((w >> 8) & 0xffu) - mean) / sd);
-    o.z = (float)(((double)((w >> 16) & 0xffu) - mean) / sd);
-    o.w = (float)(((double)(w >> 24) - mean) / sd);
+    o.x = lut[w & 0xffu]; o.y = lut[(w >> 8) & 0xffu]; o.z = lut[(w >> 16) & 0xffu]; o.w = lut[w >> 24];
     dst[i] = o;
   }
 }
