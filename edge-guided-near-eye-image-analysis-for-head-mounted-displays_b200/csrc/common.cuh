@@ -136,4 +136,39 @@ struct ConvEpi {
   // segmentation logits the reference returns, models/RITnet_v2.py:288) instead of a split-bf16 buffer
   float* logits;
   int logits_c;
+  // optional "+ bilinear x2 upsample of a half-resolution tensor" before the activation: the decoder's
+  // 1x1 convolutions over cat[upsample(x), skip] are evaluated as upsample(W_a x) + W_b skip + b
+  // (both are linear and the interpolation weights sum to one), so the upsampled x never exists
+  const bf16* up_hi;
+  const bf16* up_lo;
+  int up_C, up_coff;       // channels of the half-resolution buffer, first channel of the window
 };
+
+// v[0..NCH) += bilinear x2 upsample (F.interpolate, align_corners=False, models/RITnet_v2.py:82) of the
+// half-resolution split-bf16 tensor at output pixel (py, px) of frame n, channels [ch, ch + NCH).
+// For o = 2i: 0.25 * in[i-1] + 0.75 * in[i]; for o = 2i+1: 0.75 * in[i] + 0.25 * in[i+1], indices clamped.
+template <int NCH>
+__device__ __forceinline__ void upsample_add(const ConvEpi& e, int n, int py, int px, int H, int W, int ch, float* v) {
+  const int Hi = H >> 1, Wi = W >> 1;
+  const int i = py >> 1, j = px >> 1;
+  const int ya = (py & 1) ? i : max(i - 1, 0), yb = (py & 1) ? min(i + 1, Hi - 1) : i;
+  const int xa = (px & 1) ? j : max(j - 1, 0), xb = (px & 1) ? min(j + 1, Wi - 1) : j;
+  const float wya = (py & 1) ? 0.75f : 0.25f, wyb = 1.f - wya;
+  const float wxa = (px & 1) ? 0.75f : 0.25f, wxb = 1.f - wxa;
+  const size_t fb = (size_t)n * Hi * Wi;
+  const size_t c0 = (size_t)e.up_coff + ch;
+#pragma unroll
+  for (int g = 0; g < NCH; g += 8) {
+    float t00[8], t01[8], t10[8], t11[8];
+    load8(e.up_hi, e.up_lo, (fb + (size_t)ya * Wi + xa) * e.up_C + c0 + g, t00);
+    load8(e.up_hi, e.up_lo, (fb + (size_t)ya * Wi + xb) * e.up_C + c0 + g, t01);
+    load8(e.up_hi, e.up_lo, (fb + (size_t)yb * Wi + xa) * e.up_C + c0 + g, t10);
+    load8(e.up_hi, e.up_lo, (fb + (size_t)yb * Wi + xb) * e.up_C + c0 + g, t11);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float top = wxa * t00[k] + wxb * t01[k];
+      const float bot = wxa * t10[k] + wxb * t11[k];
+      v[g + k] += wya * top + wyb * bot;
+    }
+  }
+}

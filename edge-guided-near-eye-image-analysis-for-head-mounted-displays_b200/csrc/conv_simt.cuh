@@ -95,9 +95,11 @@ __global__ void __launch_bounds__(ST_THREADS) conv_simt_kernel(const SimtParams 
     const int ch = cb + cog * 8;
     if (valid && ch + 8 <= p.e.cout_store) {
       float v[8];
+      float up[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (p.e.up_hi) upsample_add<8>(p.e, n, lin / p.g.W, lin % p.g.W, p.g.H, p.g.W, ch, up);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        float a = acc[0][i] + p.e.bias[ch + i];
+        float a = acc[0][i] + p.e.bias[ch + i] + up[i];
         a = apply_act(a, p.e.act);
         if (p.e.post_scale) a = a * p.e.post_scale[ch + i] + p.e.post_shift[ch + i];
         v[i] = a;

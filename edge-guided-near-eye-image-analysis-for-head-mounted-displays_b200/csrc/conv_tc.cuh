@@ -287,6 +287,9 @@ __device__ __forceinline__ float warp_reduce32x32(float (&v)[32], int lane) {
 
 }  // namespace tc
 
+// UP: the layer adds the bilinear upsample of a half-resolution tensor in its epilogue (decoder 1x1
+// convolutions); a separate instantiation keeps the registers of that path out of every other layer.
+template <bool UP>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
@@ -619,6 +622,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t aphase = (p.acc_bufs == 2 ? (use >> 1) : use) & 1u;
       const int px = tx * bw + mc;
 
+      // upsample-add layers: the half-resolution operands of this warp's first two sub-tiles are
+      // requested before the accumulator is awaited, and those of every later pair right after the
+      // previous pair has been consumed, so their L2 latency hides behind TMEM loads and stores
+      float L[2][UP ? 16 : 1];
+      auto up_fetch = [&](int g, int s0) {
+        const int rw = 32 >> p.bw_log2, lcols = (bw >> 1) + 2, lrows = (rw >> 1) + 2;
+        const int Hi = p.g.H >> 1, Wi = p.g.W >> 1;
+        const int lr = min(lane / lcols, lrows - 1), lc = lane % lcols;
+        const int xx = min(max(((tx * bw) >> 1) - 1 + lc, 0), Wi - 1);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (UP && s0 + u < nsub) {
+            const int py0 = ty * p.tr + (s0 + u) * p.sr + quarter * rw;             // first output row of this warp
+            const int yy = min(max((py0 >> 1) - 1 + lr, 0), Hi - 1);
+            load16(p.e.up_hi, p.e.up_lo, (((size_t)n * Hi + yy) * Wi + xx) * p.e.up_C + p.e.up_coff + nb * p.n_tile + (g << 4), L[u]);
+          }
+        }
+      };
+      if (UP && half < (p.n_tile >> 4)) up_fetch(half, 0);
+
       mbar_wait(tfull_bar(ab), aphase, p.err_flag, 6);
       fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * TC_ACC_STRIDE;
@@ -663,8 +686,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const bool valid = (py < p.g.H) && (px < p.g.W);
                 const size_t pix = ((size_t)n * p.g.H + py) * p.g.W + px;
                 float v[16];
+                if (UP) {
+                  // + bilinear x2 upsample of the half-resolution tensor (common.cuh upsample_add): the 32
+                  // output pixels of this warp (rw rows x bw columns, rw * bw = 32) blend (rw/2 + 2) x (bw/2 + 2)
+                  // <= 30 half-resolution pixels; each lane loaded ONE of them (up_fetch: 16 channels, 2 x 32 bytes,
+                  // indices clamped like F.interpolate) and the blends are assembled with shuffles.
+                  const int lcols = (bw >> 1) + 2;
+                  const int wr = lane >> p.bw_log2;                                   // my row / column inside the warp's patch
+                  const int la = (wr >> 1) + (wr & 1), lca = (mc >> 1) + (mc & 1);    // even: (l-1, l), odd: (l, l+1) with l = (r>>1)+1
+                  const float wya = (wr & 1) ? 0.75f : 0.25f, wyb = 1.f - wya;
+                  const float wxa = (mc & 1) ? 0.75f : 0.25f, wxb = 1.f - wxa;
+                  const int s00 = la * lcols + lca, s10 = s00 + lcols;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = apply_act(__uint_as_float(r[u][i]) + bias[i], p.e.act);
+                  for (int i = 0; i < 16; ++i) {
+                    const float lv = L[u][UP ? i : 0];
+                    const float t00 = __shfl_sync(0xffffffffu, lv, s00), t01 = __shfl_sync(0xffffffffu, lv, s00 + 1);
+                    const float t10 = __shfl_sync(0xffffffffu, lv, s10), t11 = __shfl_sync(0xffffffffu, lv, s10 + 1);
+                    const float top = wxa * t00 + wxb * t01, bot = wxa * t10 + wxb * t11;
+                    v[i] = apply_act((__uint_as_float(r[u][i]) + bias[i]) + (wya * top + wyb * bot), p.e.act);
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) v[i] = apply_act(__uint_as_float(r[u][i]) + bias[i], p.e.act);
+                }
                 if (has_post) {
 #pragma unroll
                   for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], c_scale[cb + i], c_shift[cb + i]);
@@ -687,6 +731,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                   }
                 }
               }
+            }
+            if (UP) {                              // request the next pair's half-resolution operands
+              if (s0 + 2 < nsub) up_fetch(g, s0 + 2);
+              else if (g + 2 < per_sub) up_fetch(g + 2, 0);
             }
           }
           if (p.e.stats) {
@@ -917,8 +965,8 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
 static void tc_launch(const TcParams& p, int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const size_t smem = tc_smem_bytes(p);
@@ -932,7 +980,8 @@ static void tc_launch(const TcParams& p, int num_sms, cudaStream_t stream) {
     CUDA_OK(cudaMemsetAsync(buf, 0, 148 * 10 * sizeof(long long), stream));
     TcParams q = p;
     q.timing = buf;
-    conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(q);
+    if (q.e.up_hi) conv_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(q);
+    else conv_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(q);
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(stream));
     long long h[148 * 10];
@@ -943,6 +992,7 @@ static void tc_launch(const TcParams& p, int num_sms, cudaStream_t stream) {
             p.g.H, p.g.W, p.g.nchunks, p.g.ntaps, p.n_tile, p.S, p.na, p.nw, p.g.batch, a[0], a[1], a[2], a[3], a[4], a[9], a[5], a[6], a[7], a[8]);
     return;
   }
-  conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(p);
+  if (p.e.up_hi) conv_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(p);
+  else conv_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(p);
   CUDA_OK(cudaGetLastError());
 }

@@ -159,9 +159,9 @@ struct Engine {
     ConvLayer conv1, conv21, conv22, conv31, conv32, td;
   };
   struct UpBlock {
-    Act *buf, *t, *out;
-    int in_c, in_pad, out_c, out_pad, skip_c, H, W;
-    ConvLayer c11, c12, c21, c22;
+    Act *buf, *t, *out, *y;     // buf: x1; y: half-resolution [W11_a x | W21_a x] (see build_esf)
+    int in_c, out_c, out_pad, skip_c, H, W;
+    ConvLayer pre, c11, c12, c21, c22;
   };
   struct {
     int E = 0;                    // encoder frames per micro-batch
@@ -355,12 +355,12 @@ struct Engine {
     }
   }
 
-  void run_conv(ConvLayer& L, int batch, cudaStream_t st) {
+  void run_conv(ConvLayer& L, int batch, cudaStream_t st, int noff = -1) {
     if (profiling) {
       if (prof_used >= 8192) profile_resolve();
       profile_begin(st);
     }
-    run_conv_impl(L, batch, st);
+    run_conv_impl(L, batch, st, noff);
     if (profiling) profile_end(st, L.flops * batch, &L, nullptr, batch);
   }
 
@@ -744,41 +744,69 @@ struct Engine {
     const int d_in[4] = {cfg.add_edge ? 306 : 153, cfg.add_edge ? 180 : 115, cfg.add_edge ? 100 : 76, cfg.add_edge ? 62 : 38};
     const int d_out[4] = {cfg.add_edge ? 180 : 115, cfg.add_edge ? 100 : 76, cfg.add_edge ? 62 : 38, 32};
     static const char* uname[4] = {"dec.up_block4", "dec.up_block3", "dec.up_block2", "dec.up_block1"};
+    // Each up block (RITnet_v2.py:79-88) applies two 1x1 convolutions to cat[upsample2x(x), skip(, x1)].
+    // Both the bilinear interpolation and the 1x1 convolution are linear and the interpolation weights
+    // sum to one, so  W . cat[up(x), rest] + b  =  up(W_a x) + W_b rest + b :  `pre` evaluates
+    // [W11_a ; W21_a] x once at HALF resolution and conv11 / conv21 add its bilinear upsample in their
+    // epilogues.  The upsampled x (up to 320 channels at the skip's resolution) is never materialised.
     for (int i = 0; i < 4; ++i) {
       UpBlock& u = es.up[i];
       Block& sk = es.blk[3 - i];
       u.in_c = d_in[i]; u.out_c = d_out[i]; u.out_pad = round_up(d_out[i], 16);
-      // the upsampled input occupies [0, in_pad); with add_edge the first block's input is
-      // cat(x, x_edge) (RITnet_v2.py:286) and each 153-channel half gets its own 8-aligned slot
-      const bool two_halves = (i == 0 && cfg.add_edge);
-      u.in_pad = two_halves ? 2 * 160 : round_up(d_in[i], 16);
       u.skip_c = sk.inter + sk.in_c; u.H = sk.H; u.W = sk.W;
-      u.buf = new_act(mem, mb, u.H, u.W, u.in_pad + u.out_pad);
+      u.buf = new_act(mem, mb, u.H, u.W, u.out_pad);
       u.t = new_act(mem, mb, u.H, u.W, u.out_pad);
       u.out = new_act(mem, mb, u.H, u.W, u.out_pad);
+      u.y = new_act(mem, mb, u.H / 2, u.W / 2, 2 * u.out_pad);
       const std::string P = uname[i];
       debug_acts[P + ".out"] = {u.out, {0, u.out_c}};
-      debug_acts[P + ".up"] = {u.buf, {0, u.in_c}};
       auto W = [&](const std::string& n) -> const HostTensor& { return sd_get(sd, P + "." + n + ".weight"); };
       auto Bv = [&](const std::string& n) -> const HostTensor& { return sd_get(sd, P + "." + n + ".bias"); };
+      const HostTensor& w11 = W("conv11");
+      const HostTensor& w21 = W("conv21");
+      const int k11 = u.in_c + u.skip_c, k21 = k11 + u.out_c;
+      EGN_CHECK(w11.shape[0] == u.out_c && w11.shape[1] == k11 && w21.shape[0] == u.out_c && w21.shape[1] == k21,
+                P + ": unexpected 1x1 weight shapes");
+      // half-resolution part: rows [0, out_c) <- W11[:, :in_c], rows [out_pad, out_pad + out_c) <- W21[:, :in_c]
+      std::vector<float> w_pre((size_t)2 * u.out_pad * u.in_c, 0.f), w11s((size_t)u.out_c * u.skip_c), w21s((size_t)u.out_c * (u.skip_c + u.out_c));
+      for (int co = 0; co < u.out_c; ++co) {
+        for (int c = 0; c < u.in_c; ++c) {
+          w_pre[(size_t)co * u.in_c + c] = w11.data[(size_t)co * k11 + c];
+          w_pre[(size_t)(u.out_pad + co) * u.in_c + c] = w21.data[(size_t)co * k21 + c];
+        }
+        for (int c = 0; c < u.skip_c; ++c) w11s[(size_t)co * u.skip_c + c] = w11.data[(size_t)co * k11 + u.in_c + c];
+        for (int c = 0; c < u.skip_c + u.out_c; ++c) w21s[(size_t)co * (u.skip_c + u.out_c) + c] = w21.data[(size_t)co * k21 + u.in_c + c];
+      }
+      std::vector<Piece> xin;
+      if (i == 0) {
+        xin.push_back({es.bt, 0, 153, 0});
+        if (cfg.add_edge) xin.push_back({es.bt, 0, 153, mb});     // x = cat(x, x_edge) (RITnet_v2.py:286); offset patched per launch
+      } else {
+        xin.push_back({es.up[i - 1].out, 0, u.in_c, 0});
+      }
+      build_conv(u.pre, mem, P + ".pre", xin, {{w_pre.data(), nullptr, 1, 0}}, 2 * u.out_pad, u.in_c, 1, 1, u.H / 2, u.W / 2, mb);
+      set_store_epilogue(u.pre, u.y, 0, ACT_NONE);
+      u.pre.flops = 0;                                           // counted with conv11 / conv21 at the reference's sizes
+      finalize_conv(u.pre);
       std::vector<Piece> x;
-      if (two_halves) { x.push_back({u.buf, 0, 153, 0}); x.push_back({u.buf, 160, 153, 0}); }
-      else x.push_back({u.buf, 0, u.in_c, 0});
       x.push_back({sk.buf, sk.off_out, sk.inter, 0});
       x.push_back({sk.buf, sk.off_x, sk.in_c, 0});
-      build_conv(u.c11, mem, P + ".conv11", x, {{W("conv11").data.data(), Bv("conv11").data.data(), 1, 0}}, u.out_c,
-                 u.in_c + u.skip_c, 1, 1, u.H, u.W, mb);
+      build_conv(u.c11, mem, P + ".conv11", x, {{w11s.data(), Bv("conv11").data.data(), 1, 0}}, u.out_c, u.skip_c, 1, 1, u.H, u.W, mb);
       set_store_epilogue(u.c11, u.t, 0, ACT_NONE);
+      u.c11.e.up_hi = u.y->hi; u.c11.e.up_lo = u.y->lo; u.c11.e.up_C = u.y->C; u.c11.e.up_coff = 0;
+      u.c11.flops = 2.0 * u.out_c * k11 * u.H * u.W;
       finalize_conv(u.c11);
       build_conv(u.c12, mem, P + ".conv12", {{u.t, 0, u.out_c, 0}}, {{W("conv12").data.data(), Bv("conv12").data.data(), 1, 1}},
                  u.out_c, u.out_c, 3, 3, u.H, u.W, mb);
-      set_store_epilogue(u.c12, u.buf, u.in_pad, ACT_LRELU);
+      set_store_epilogue(u.c12, u.buf, 0, ACT_LRELU);
       finalize_conv(u.c12);
       std::vector<Piece> x21 = x;
-      x21.push_back({u.buf, u.in_pad, u.out_c, 0});
-      build_conv(u.c21, mem, P + ".conv21", x21, {{W("conv21").data.data(), Bv("conv21").data.data(), 1, 0}}, u.out_c,
-                 u.in_c + u.skip_c + u.out_c, 1, 1, u.H, u.W, mb);
+      x21.push_back({u.buf, 0, u.out_c, 0});
+      build_conv(u.c21, mem, P + ".conv21", x21, {{w21s.data(), Bv("conv21").data.data(), 1, 0}}, u.out_c, u.skip_c + u.out_c, 1, 1,
+                 u.H, u.W, mb);
       set_store_epilogue(u.c21, u.t, 0, ACT_NONE);
+      u.c21.e.up_hi = u.y->hi; u.c21.e.up_lo = u.y->lo; u.c21.e.up_C = u.y->C; u.c21.e.up_coff = u.out_pad;
+      u.c21.flops = 2.0 * u.out_c * k21 * u.H * u.W;
       finalize_conv(u.c21);
       build_conv(u.c22, mem, P + ".conv22", {{u.t, 0, u.out_c, 0}}, {{W("conv22").data.data(), Bv("conv22").data.data(), 1, 1}},
                  u.out_c, u.out_c, 3, 3, u.H, u.W, mb);
@@ -981,21 +1009,7 @@ struct Engine {
       // ---- decoder
       for (int i = 0; i < 4; ++i) {
         UpBlock& u = es.up[i];
-        if (profiling) { if (prof_used >= 8192) profile_resolve(); profile_begin(st); }
-        UpsampleParams up;
-        up.B = nb; up.Hi = u.H / 2; up.Wi = u.W / 2;
-        if (i == 0) {
-          up.src = make_view(*es.bt, 0, 0); up.dst = make_view(*u.buf, 0); up.Cs = 160;
-          launch_1d(upsample2x_kernel, up, (long long)nb * up.Hi * up.Wi * (up.Cs / 8), st); ++launches;
-          if (cfg.add_edge) {                                 // x = cat(x, x_add)  RITnet_v2.py:286
-            up.src = make_view(*es.bt, 0, eoff); up.dst = make_view(*u.buf, 160);
-            launch_1d(upsample2x_kernel, up, (long long)nb * up.Hi * up.Wi * (up.Cs / 8), st); ++launches;
-          }
-        } else {
-          up.src = make_view(*es.up[i - 1].out, 0); up.dst = make_view(*u.buf, 0); up.Cs = es.up[i - 1].out_pad;
-          launch_1d(upsample2x_kernel, up, (long long)nb * up.Hi * up.Wi * (up.Cs / 8), st); ++launches;
-        }
-        if (profiling) profile_end(st, 0, nullptr, "esf.upsample", 0);
+        run_conv(u.pre, nb, st, (i == 0 && cfg.add_edge) ? eoff : -1);
         run_conv(u.c11, nb, st);
         run_conv(u.c12, nb, st);
         run_conv(u.c21, nb, st);

@@ -384,3 +384,48 @@ def test_forward_loss_slot(env):
                 cond.to(dev), torch.zeros(4, dtype=torch.long, device=dev), 0.5)
     assert out[3].shape == (1,) and out[3].is_cuda
     assert float(out[3].item()) == pytest.approx(float(want), rel=5e-3)
+
+
+def test_config0_baseline_batch16_calc_acc(env, capsys):
+    """BASELINE.json configs[0]: configs/baseline.yaml (no edge input to the net), batch 16, through the
+    calc_acc path - the engine against the oracle on labelled synthetic eyes, at BASELINE's bars."""
+    egn, g, synth, dev = env["egn"], env["graph"], env["synth"], env["dev"]
+    m, st, esd = _model(env, "baseline", mb=16)
+    keys = ("img", "label", "spatW", "distMap", "pupil_center", "iris_center", "elNorm", "cond", "imInfo")
+    eb = synth.synthetic_eye_batch(700, 16)
+    batch = tuple(torch.from_numpy(eb[k]) for k in keys)
+    em = egn.BDCN(); em.load_state_dict(env["bsd"]); em = em.cuda().eval(); em.micro_batch = 16
+    out = egn.calc_acc(None, [batch], m, em, dev, return_all=True)
+    capsys.readouterr()
+    with torch.no_grad():
+        ref = g.esf_forward(esd, st, batch[0], None)
+    pref = g.get_predictions(ref["op"]).numpy()
+    c = eb["cond"]
+    ious_ref = g.seg_metrics(eb["label"], pref, c[:, 1])[1]
+    assert np.abs(out[0] - ious_ref).max() * 100 < 0.1
+    want = (g.point_metric(eb["pupil_center"], ref["elOut"][:, 5:7].numpy(), c[:, 0], (240, 320))[0],
+            g.point_metric(eb["iris_center"], ref["elOut"][:, 0:2].numpy(), c[:, 1], (240, 320))[0],
+            g.point_metric(eb["pupil_center"], ref["elPred"][:, 5:7].numpy(), c[:, 1], (240, 320))[0],
+            g.point_metric(eb["iris_center"], ref["elPred"][:, 0:2].numpy(), c[:, 1], (240, 320))[0])
+    for got, w in zip(out[1:], want):
+        assert abs(got - w) < 0.25
+
+
+def test_batch_of_one_shapes_and_int_id(env):
+    """evaluate.py:115-131 calls the model with B == 1, ID == 0 (an int) and zero-filled targets; the
+    reference squeezes / unsqueezes around that case (loss.py:42, RITnet_v2.py:409-412) and still returns
+    [1,3,H,W], [1,10], [1,153], [1], [1,10]."""
+    egn, dev = env["egn"], env["dev"]
+    m, st, esd = _model(env, "baseline_edge", mb=1)
+    x = env["img"][:1].to(dev)
+    e = env["edge_ref"][:1].to(dev)
+    labels = torch.zeros((1, 240, 320), device=dev)
+    labels[..., 0, 2] = 1; labels[..., 2, 2] = 2
+    with torch.no_grad():
+        op, elPred, latent, loss, elOut = m(x, e, labels.long(), torch.zeros((1, 2), device=dev),
+                                            torch.zeros((1, 2, 5), device=dev), torch.zeros((1, 240, 320), device=dev),
+                                            torch.zeros((1, 3, 240, 320), device=dev), torch.zeros((1, 4), device=dev), 0, 0)
+    assert op.shape == (1, 3, 240, 320) and elPred.shape == (1, 10) and latent.shape == (1, 153)
+    assert loss.shape == (1,) and elOut.shape == (1, 10) and torch.isfinite(loss).all()
+    gold = np.load(os.path.join(env["golden"], "fwd_baseline_edge.npz"))
+    assert (egn.get_predictions(op, m).numpy()[0] == gold["pred"][0]).mean() >= 0.999

@@ -1,12 +1,12 @@
 """Runs the ESF-Net (baseline_edge) forward twice on a small batch so that ncu can capture single
 conv_tc_kernel launches of the second (warm) pass:
 
-    ncu --set full --clock-control none --import-source on -k regex:conv_tc -s <50 + i> -c <n> \
+    ncu --set full --clock-control none --import-source on -k regex:conv_tc -s <54 + i> -c <n> \
         -o gpurun_out/prof python tools/profile_layer.py [esf|bdcn] [batch]
 
 conv_tc launch order, ESF: 0 enc.head.conv2, then per encoder block conv1, conv21, conv22, conv31,
-conv32, TD.conv (1..30), then per up block conv11, conv12, conv21, conv22 (31..46), 47 dec.final.conv1,
-48 dec.final.conv2, 49 elReg.c1.
+conv32, TD.conv (1..30), then per up block pre, conv11, conv12, conv21, conv22 (31..50), 51 dec.final.conv1,
+52 dec.final.conv2, 53 elReg.c1.
 BDCN: per VGG layer i: [features.conv(i) for i>0], msblock.conv, msblock.tail (38 launches)."""
 import os
 import sys

@@ -21,14 +21,14 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-fil
 # 2. DRAM traffic + duration of every conv_tc launch of one warm pass per net
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv_tc -s 38 -c 38 \
     --csv --log-file $O/${R}_conv_dram_bdcn.csv python tools/profile_layer.py bdcn 16 > /dev/null 2>&1
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv_tc -s 50 -c 50 \
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv_tc -s 54 -c 54 \
     --csv --log-file $O/${R}_conv_dram_esf.csv python tools/profile_layer.py esf 16 > /dev/null 2>&1
 # 3. full captures: first six BDCN conv launches of the warm pass (msblock1_1.conv, .tail, conv1_2, msblock1_2.conv, .tail,
-#    conv2_1), conv3_2 (launch 14), and the first seven ESF conv launches (50 conv_tc launches per ESF pass since dec.final.conv2 moved to the tensor cores) (head.conv2, down_block1.{conv1,conv21,conv22,conv31,conv32,TD})
+#    conv2_1), conv3_2 (launch 14), and the first seven ESF conv launches (54 conv_tc launches per ESF pass: dec.final.conv2 and the four half-resolution decoder pre-convolutions included) (head.conv2, down_block1.{conv1,conv21,conv22,conv31,conv32,TD})
 full conv_bdcn conv_tc 38 6 python tools/profile_layer.py bdcn 16
 full conv_vgg3_2 conv_tc 52 1 python tools/profile_layer.py bdcn 16
-full conv_esf conv_tc 50 7 python tools/profile_layer.py esf 16
+full conv_esf conv_tc 54 7 python tools/profile_layer.py esf 16
 # 4. the bandwidth-bound helpers of one warm pass
-full aux_esf "instnorm|upsample|last_conv|first_conv|head_tail|spatial_mean" 19 19 python tools/profile_layer.py esf 16
+full aux_esf "instnorm|first_conv|head_tail|spatial_mean" 14 14 python tools/profile_layer.py esf 16
 full aux_bdcn "first_conv|maxpool|bdcn_tail" 6 6 python tools/profile_layer.py bdcn 16
 du -sh $O; ls $O | head -30

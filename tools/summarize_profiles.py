@@ -26,7 +26,7 @@ ESF_ORDER = ["enc.head.conv2"]
 for b in ["down_block1", "down_block2", "down_block3", "down_block4", "bottleneck"]:
     ESF_ORDER += ["enc.%s.%s" % (b, c) for c in ["conv1", "conv21", "conv22", "conv31", "conv32", "TD.conv"]]
 for b in ["up_block4", "up_block3", "up_block2", "up_block1"]:
-    ESF_ORDER += ["dec.%s.%s" % (b, c) for c in ["conv11", "conv12", "conv21", "conv22"]]
+    ESF_ORDER += ["dec.%s.%s" % (b, c) for c in ["pre", "conv11", "conv12", "conv21", "conv22"]]
 ESF_ORDER += ["dec.final.conv1", "dec.final.conv2", "elReg.c1"]
 
 
