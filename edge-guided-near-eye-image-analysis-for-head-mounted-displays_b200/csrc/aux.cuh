@@ -217,59 +217,6 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const NormApplyPara
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// F.interpolate(bilinear, align_corners=False, scale_factor=2) (RITnet_v2.py:80-83).
-// One thread per (output pixel, channel); `Cs` real channels are written at dst.coff.
-struct UpsampleParams {
-  View src, dst;
-  int B, Hi, Wi, Cs;
-};
-
-__global__ void __launch_bounds__(256) upsample2x_kernel(const UpsampleParams p) {
-  // one thread per (INPUT pixel, 8-channel group): with scale 2 and half-pixel centres the four
-  // outputs (2i..2i+1, 2j..2j+1) are 0.75/0.25 blends of the 3x3 input neighbourhood (clamped at the
-  // borders), so 9 loads serve 4 stores; Cs is a multiple of 8 (padded channels are zero)
-  const int groups = p.Cs / 8;
-  const long long total = (long long)p.B * p.Hi * p.Wi * groups;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int gidx = (int)(idx % groups);
-  const long long pix = idx / groups;
-  const int j = (int)(pix % p.Wi);
-  const int i = (int)((pix / p.Wi) % p.Hi);
-  const int n = (int)(pix / ((long long)p.Wi * p.Hi));
-  const int im = max(i - 1, 0), ip = min(i + 1, p.Hi - 1);
-  const int jm = max(j - 1, 0), jp = min(j + 1, p.Wi - 1);
-  const size_t fb = (size_t)(n + p.src.n_off) * p.Hi * p.Wi;
-  const size_t cb = p.src.coff + gidx * 8;
-  float t[3][3][8];
-  const int ys[3] = {im, i, ip}, xs[3] = {jm, j, jp};
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int b = 0; b < 3; ++b) load8(p.src.hi, p.src.lo, (fb + (size_t)ys[a] * p.Wi + xs[b]) * p.src.C + cb, t[a][b]);
-  const int Ho = p.Hi * 2, Wo = p.Wi * 2;
-  // F.interpolate(align_corners=False): source coordinate (o + 0.5) / 2 - 0.5 clamped at 0 -> for
-  // o = 2i: 0.25 * in[i-1] + 0.75 * in[i] (in[0] alone at o = 0); for o = 2i+1: 0.75 * in[i] + 0.25 * in[i+1]
-#pragma unroll
-  for (int dy = 0; dy < 2; ++dy) {
-    const int ya = dy == 0 ? 0 : 1, yb = dy == 0 ? 1 : 2;          // rows blended: (ya, yb)
-    const float wya = dy == 0 ? 0.25f : 0.75f, wyb = 1.f - wya;
-#pragma unroll
-    for (int dx = 0; dx < 2; ++dx) {
-      const int xa = dx == 0 ? 0 : 1, xb = dx == 0 ? 1 : 2;
-      const float wxa = dx == 0 ? 0.25f : 0.75f, wxb = 1.f - wxa;
-      float v[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float top = wxa * t[ya][xa][k] + wxb * t[ya][xb][k];
-        const float bot = wxa * t[yb][xa][k] + wxb * t[yb][xb][k];
-        v[k] = wya * top + wyb * bot;
-      }
-      store8(p.dst.hi, p.dst.lo, ((size_t)(n + p.dst.n_off) * Ho * Wo + (size_t)(2 * i + dy) * Wo + 2 * j + dx) * p.dst.C + p.dst.coff + gidx * 8, v);
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------
 // Spatial mean of a channel window -> fp32 [B][Cs]  (latent, RITnet_v2.py:282).

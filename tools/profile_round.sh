@@ -15,9 +15,10 @@ full() {   # name, kernel regex, skip, count, command...
   ncu -i $O/${R}_$name.ncu-rep --page source --csv --launch-skip 0 --launch-count 1 > $O/${R}_${name}_source0.csv 2>/dev/null
   rm -f $O/${R}_$name.ncu-rep
 }
-# 1. every launch of one small step with its device time (cold-cache, serialised: compare shares)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $O/${R}_launches.csv \
-    python bench.py --batch 16 --micro-batch 16 --steps 1 --warmup 1 --no-cpu-baseline > $O/${R}_launches.log 2>&1
+# 1. every launch of bench.py's own command (warm-up step + the two timed steps = 3 x 2 micro-batches of 128 frames)
+#    with its device time (cold-cache, serialised: compare shares with roofline.kernel_share_of_step, not absolutes)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 960 --csv --log-file $O/${R}_launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/${R}_launches.log 2>&1
 # 2. DRAM traffic + duration of every conv_tc launch of one warm pass per net
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv_tc -s 38 -c 38 \
     --csv --log-file $O/${R}_conv_dram_bdcn.csv python tools/profile_layer.py bdcn 16 > /dev/null 2>&1

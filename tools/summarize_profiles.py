@@ -49,7 +49,7 @@ def launches():
         agg[n][0] += 1
         agg[n][1] += v
     tot = sum(v[1] for v in agg.values())
-    out = ["# %s: every kernel launch of `bench.py --batch 16 --micro-batch 16 --steps 1 --warmup 1` under" % R,
+    out = ["# %s: the first 960 kernel launches (warm-up step + both timed steps) of `bench.py --steps 2 --warmup 1` under" % R,
            "# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: shares, not absolutes)",
            "kernel,launches,total_us,share"]
     for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
