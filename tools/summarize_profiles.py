@@ -46,6 +46,10 @@ def launches():
         except Exception:
             continue
         n = r[iname].split("(")[0]
+        if n.startswith("void "):
+            n = n[5:]
+        if n.startswith("conv_tc_kernel"):          # <false> plain / <true> upsample-add epilogue instantiations
+            n = "conv_tc_kernel"
         agg[n][0] += 1
         agg[n][1] += v
     tot = sum(v[1] for v in agg.values())
