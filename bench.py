@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="egn", choices=["egn", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
-    ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("EGN_MICRO_BATCH", "128")))
+    ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("EGN_MICRO_BATCH", "256")))
     ap.add_argument("--config", default="baseline_edge")
     ap.add_argument("--cpu-frames", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -268,14 +268,18 @@ def main():
                 "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (all %d conv launches of the timed region)" % conv_n,
                              "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                              "peak_source": peak_src,
-                             "traffic": (traffic or {}).get("dram_bytes_per_launch"),
-                             "traffic_note": (traffic or {}).get("note", "no ncu capture committed yet"),
+                             # the capture ran 16-frame launches; a launch of this run carries micro_batch frames
+                             "traffic": ((traffic["dram_bytes_per_launch"] * min(args.micro_batch, B) / float(traffic.get("frames", 16)))
+                                         if traffic else None),
+                             "traffic_note": ((traffic["note"] + "; scaled here to %d-frame launches" % min(args.micro_batch, B))
+                                              if traffic else "no ncu capture committed yet"),
                              "algorithmic_flops_per_launch": conv_flops / conv_n if conv_n else None,
                              "ms_per_launch": conv_ms / conv_n if conv_n else None,
                              "kernel_share_of_step": conv_ms / ms if ms > 0 else None,
                              "whole_step_tflops": fps / world * gf / 1000.0 if gf else None,
                              "whole_step_frac": fps / world * gf / 1000.0 / peak_tf if gf else None},
                 "clocks": sampler.summary(),
+                "hbm_used_gb": round((torch.cuda.mem_get_info(dev)[1] - torch.cuda.mem_get_info(dev)[0]) / 1e9, 1),
                 "metrics_check": acc.result()["frames"]}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

@@ -36,6 +36,7 @@ struct TcParams {
   int nsplit;                          // 1: hi*hi only, 3: split product
   int n_tile, n_blocks, tiles_x, tiles_y, total_tiles;
   int bw_log2, sr, S, tr, dmax, box_rows;
+  int xshare, box_w, dxmax;            // xshare: ONE (bw + 2*dxmax)-pixel-wide box per chunk serves every horizontal tap offset
   int na, nw;                          // A / W ring depths
   int wide_b;                          // 1: hi*hi and hi*lo issue as ONE MMA of N = 2*n_tile against the stacked [W_hi; W_lo] tile (A_hi read once)
   int w_box;                           // 1: a W slot holds every tap of an activation box (one barrier round trip per box)
@@ -144,11 +145,14 @@ __device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
 }
 
 // K-major, 64-byte swizzle: rows of 64 B (32 bf16), 8-row atoms 512 B apart (SBO), version 1.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+// `sbo`: bytes between consecutive 8-row groups.  The start address need not be aligned to the 512-byte
+// swizzle atom and sbo may be any multiple of 64: the XOR pattern is a function of the absolute
+// shared-memory address (tools/desc_shift_probe.cu), which the shared activation box relies on.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo = 512) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(512 >> 4) << 32;        // stride byte offset
+  d |= (uint64_t)(sbo >> 4) << 32;        // stride byte offset
   d |= (uint64_t)1 << 46;                 // descriptor version
   d |= (uint64_t)4 << 61;                 // SWIZZLE_64B
   return d;
@@ -205,9 +209,9 @@ __device__ __forceinline__ bool elect_one() {
 template <int NSUB, int NPL, int WIDE>
 __device__ __forceinline__ void issue_tap(uint32_t sA, uint32_t a_plane, uint32_t sW, uint32_t w_plane,
                                           uint32_t d_tmem, uint32_t sub_cols, uint32_t idesc, uint32_t idesc_wide,
-                                          uint32_t first) {
-  const uint64_t dA_hi = make_desc(sA), dW_hi = make_desc(sW);
-  const uint64_t dA_lo = make_desc(sA + a_plane), dW_lo = make_desc(sW + w_plane);
+                                          uint32_t first, uint32_t a_sbo, uint32_t a_sub16) {
+  const uint64_t dA_hi = make_desc(sA, a_sbo), dW_hi = make_desc(sW);
+  const uint64_t dA_lo = make_desc(sA + a_plane, a_sbo), dW_lo = make_desc(sW + w_plane);
 #pragma unroll
   for (int k = 0; k < EGN_KC / 16; ++k) {
     const uint64_t koff = (uint64_t)((k * 32) >> 4);        // 16 bf16 = 32 bytes along K
@@ -216,21 +220,21 @@ __device__ __forceinline__ void issue_tap(uint32_t sA, uint32_t a_plane, uint32_
       // A_hi x [W_hi; W_lo] -> columns [0, n) += hi*hi, [n, 2n) += hi*lo ; A_lo x W_hi -> columns [0, n)
 #pragma unroll
       for (int s = 0; s < NSUB; ++s)
-        mma_bf16(d_tmem + s * sub_cols, dA_hi + koff + (uint64_t)(s * (8192 >> 4)), dW_hi + koff, idesc_wide, acc);
+        mma_bf16(d_tmem + s * sub_cols, dA_hi + koff + (uint64_t)(s * a_sub16), dW_hi + koff, idesc_wide, acc);
 #pragma unroll
       for (int s = 0; s < NSUB; ++s)
-        mma_bf16(d_tmem + s * sub_cols, dA_lo + koff + (uint64_t)(s * (8192 >> 4)), dW_hi + koff, idesc, 1u);
+        mma_bf16(d_tmem + s * sub_cols, dA_lo + koff + (uint64_t)(s * a_sub16), dW_hi + koff, idesc, 1u);
     } else {
 #pragma unroll
       for (int s = 0; s < NSUB; ++s)
-        mma_bf16(d_tmem + s * sub_cols, dA_hi + koff + (uint64_t)(s * (8192 >> 4)), dW_hi + koff, idesc, acc);
+        mma_bf16(d_tmem + s * sub_cols, dA_hi + koff + (uint64_t)(s * a_sub16), dW_hi + koff, idesc, acc);
       if (NPL == 2) {
 #pragma unroll
         for (int s = 0; s < NSUB; ++s)
-          mma_bf16(d_tmem + s * sub_cols, dA_lo + koff + (uint64_t)(s * (8192 >> 4)), dW_hi + koff, idesc, 1u);
+          mma_bf16(d_tmem + s * sub_cols, dA_lo + koff + (uint64_t)(s * a_sub16), dW_hi + koff, idesc, 1u);
 #pragma unroll
         for (int s = 0; s < NSUB; ++s)
-          mma_bf16(d_tmem + s * sub_cols, dA_hi + koff + (uint64_t)(s * (8192 >> 4)), dW_lo + koff, idesc, 1u);
+          mma_bf16(d_tmem + s * sub_cols, dA_hi + koff + (uint64_t)(s * a_sub16), dW_lo + koff, idesc, 1u);
       }
     }
   }
@@ -343,7 +347,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   if ((int)threadIdx.x < p.g.ntaps) {
     const int t = threadIdx.x;
     TcTapStep st;
-    st.a_off = (uint32_t)((p.g.tap_dy[t] + p.dmax) << p.bw_log2) * 64u;
+    st.a_off = p.xshare ? (uint32_t)((p.g.tap_dy[t] + p.dmax) * p.box_w + p.g.tap_dx[t] + p.dxmax) * 64u
+                        : (uint32_t)((p.g.tap_dy[t] + p.dmax) << p.bw_log2) * 64u;
     st.d_col = (uint32_t)(p.g.tap_grp[t] * p.n_tile * (p.wide_b ? 2 : 1));
     st.flags = 0; st.pad = 0;
     for (int l = 0; l < p.n_aloads; ++l) {
@@ -472,6 +477,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t idesc_wide = (1u << 4) | (1u << 7) | (1u << 10) |
                                   ((uint32_t)((2 * p.n_tile) >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t sub_cols = (uint32_t)(p.g.groups * p.n_tile * (p.wide_b ? 2 : 1));
+      // shared box: consecutive 8-pixel groups of a sub-tile are consecutive image rows, box_w pixels apart
+      const uint32_t a_sbo = p.xshare ? (uint32_t)p.box_w * 64u : 512u;
+      const uint32_t a_sub16 = (p.xshare ? (uint32_t)(p.sr * p.box_w) * 64u : 8192u) >> 4;
       const int nchunks = p.g.nchunks, ntaps = p.g.ntaps;
       const uint32_t a_plane = p.a_plane_bytes, w_plane = p.w_plane_bytes;
       const int dbg = p.dbg;
@@ -520,7 +528,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         const TcTapStep cur = nxt;
                         if (j + 1 < nrun) nxt = s_tap[ld.tap0 + t0 + j + 1];
                         const uint32_t first = (c == 0 && (cur.flags & 4u)) ? 1u : 0u;
-                        issue_tap<NSUB, NPL, WIDE>(sA + cur.a_off, a_plane, sW + j * w_tap_bytes, w_plane, d_base + cur.d_col, sub_cols, idesc, idesc_wide, first);
+                        issue_tap<NSUB, NPL, WIDE>(sA + cur.a_off, a_plane, sW + j * w_tap_bytes, w_plane, d_base + cur.d_col, sub_cols, idesc, idesc_wide, first, a_sbo, a_sub16);
                       }
                     }
                     if (tm) { const long long now = clock64(); tm_i += now - tm_c0; tm_c0 = now; }
@@ -556,7 +564,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               const uint32_t first = (c == 0 && (cur.flags & 4u)) ? 1u : 0u;
               if (elect_one()) {
                 if (!(dbg & 2))
-                  issue_tap<NSUB, NPL, WIDE>(sA + cur.a_off, a_plane, sW, w_plane, d_base + cur.d_col, sub_cols, idesc, idesc_wide, first);
+                  issue_tap<NSUB, NPL, WIDE>(sA + cur.a_off, a_plane, sW, w_plane, d_base + cur.d_col, sub_cols, idesc, idesc_wide, first, a_sbo, a_sub16);
                 if (tm) { const long long now = clock64(); tm_i += now - tm_c0; tm_c0 = now; }
                 mma_commit(w_empty(ws));             // frees the weight slot when these MMAs retire
                 if (cur.flags & 2u) mma_commit(a_empty(as));   // last tap of this box
@@ -831,13 +839,13 @@ static PFN_encodeTiled get_encode_fn() {
 // promo64: the layer reads a channel window of this buffer that does not start/end on 128-byte
 // boundaries, so 128-byte L2 promotion would pull the neighbouring (unread) channels from HBM
 // (measured on enc.down_block1.conv21: 39 MB/frame of DRAM reads for 19.7 MB of operands).
-static void make_act_map(CUtensorMap* map, const bf16* ptr, int N, int H, int W, int C, int bw, int box_rows,
+static void make_act_map(CUtensorMap* map, const bf16* ptr, int N, int H, int W, int C, int box_w, int box_rows,
                          bool promo64 = false) {
   EGN_CHECK(C % 8 == 0, "activation channels must be a multiple of 8");
   EGN_CHECK(box_rows >= 1 && box_rows <= 256, "activation box rows out of range");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {EGN_KC, (cuuint32_t)bw, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[4] = {EGN_KC, (cuuint32_t)box_w, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   // tuning knob: L2 promotion of the activation boxes (0 none, 1 64 B, 2 128 B, 3 256 B)
   static const int promo_env = getenv("EGN_TC_L2PROMO") ? atoi(getenv("EGN_TC_L2PROMO")) : -1;
@@ -881,9 +889,25 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   EGN_CHECK(cout_pad % (16 * p.n_blocks) == 0, "cout_pad must split into equal 16-aligned N tiles");
   p.n_tile = cout_pad / p.n_blocks;
   EGN_CHECK(p.n_tile % 16 == 0 && p.n_tile <= 256, "bad n_tile");
+  // shared activation box (3x3 layers, dilation <= 2): one (8 + 2*dxmax)-pixel-wide box per K chunk
+  // serves every tap; needs 16-row x 8-pixel sub-tiles so that the 8-pixel groups are uniformly strided
+  int dxmax = 0, dymax = 0, ndx = 0;
+  {
+    int seen[64]; int ns = 0;
+    for (int t = 0; t < g.ntaps; ++t) {
+      dxmax = std::max(dxmax, std::abs((int)g.tap_dx[t])); dymax = std::max(dymax, std::abs((int)g.tap_dy[t]));
+      bool f = false;
+      for (int k = 0; k < ns; ++k) f |= seen[k] == g.tap_dx[t];
+      if (!f && ns < 64) seen[ns++] = g.tap_dx[t];
+    }
+    ndx = ns;
+  }
+  p.xshare = (ndx > 1 && dxmax <= 2 && dymax <= 2 && g.groups == 1 && !getenv("EGN_TC_NO_XSHARE")) ? 1 : 0;
+  p.dxmax = dxmax;
   // sub-tile shape: 8 rows x 16 px or 16 rows x 8 px, whichever covers the frame with less padding
   auto padded = [&](int bw) { const int sr = 128 / bw; return (long long)round_up(g.W, bw) * round_up(g.H, sr); };
-  const int bw = padded(8) < padded(16) ? 8 : 16;
+  if (padded(8) > padded(16)) p.xshare = 0;      // 120x160: 16-row sub-tiles would waste 6.7 % of the MMAs
+  const int bw = p.xshare ? 8 : (padded(8) < padded(16) ? 8 : 16);
   p.bw_log2 = bw == 8 ? 3 : 4;
   p.sr = 128 / bw;
   // latency mode (streaming micro-batches of a few frames, evaluate.py's per-image path): when the
@@ -919,11 +943,16 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   p.tiles_x = ceil_div(g.W, bw);
   p.tiles_y = ceil_div(g.H, p.tr);
   p.total_tiles = p.tiles_x * p.tiles_y * g.batch * p.n_blocks;
-  // A boxes: one per distinct dx, covering every dy
+  // A boxes: one per distinct dx, covering every dy (or a single wide one, see xshare)
   p.dmax = 0;
   p.n_aloads = 0;
   for (int t = 0; t < g.ntaps; ++t) {
     p.dmax = std::max(p.dmax, std::abs((int)g.tap_dy[t]));
+    if (p.xshare) {
+      if (p.n_aloads == 0) { p.aload_dx[0] = (int8_t)(-dxmax); p.aload_tap0[0] = 0; p.aload_ntaps[0] = 0; p.n_aloads = 1; }
+      ++p.aload_ntaps[0];
+      continue;
+    }
     if (p.n_aloads == 0 || p.aload_dx[p.n_aloads - 1] != g.tap_dx[t]) {
       for (int l = 0; l < p.n_aloads; ++l) EGN_CHECK(p.aload_dx[l] != g.tap_dx[t], "taps must be grouped by dx");
       EGN_CHECK(p.n_aloads < TC_MAX_ALOADS, "too many distinct horizontal tap offsets");
@@ -940,7 +969,8 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   if (const char* e = getenv("EGN_TC_PREFETCH")) p.l2_prefetch = atoi(e);
   p.dbg = 0;
   if (const char* e = getenv("EGN_TC_DBG")) p.dbg = atoi(e);
-  p.a_box_bytes = (uint32_t)p.box_rows * bw * 64u;
+  p.box_w = p.xshare ? bw + 2 * dxmax : bw;
+  p.a_box_bytes = (uint32_t)p.box_rows * p.box_w * 64u;
   p.a_plane_bytes = (p.a_box_bytes + 1023u) & ~1023u;
   p.w_plane_bytes = (uint32_t)p.n_tile * 64u;
   const int nplanes = nsplit == 1 ? 1 : 2;

@@ -343,8 +343,8 @@ struct Engine {
         //  the wider promotion is the faster one - measured on enc.down_block3.conv21/conv31)
         const bool promo64 = a->H * a->W >= 120 * 160 &&
                              ((lo * 2) % 128 != 0 || ((hi * 2) % 128 != 0 && hi != a->C));
-        make_act_map(&L.tc.a_map[0][s], a->hi, a->N, a->H, a->W, a->C, 1 << L.tc.bw_log2, L.tc.box_rows, promo64);
-        make_act_map(&L.tc.a_map[1][s], a->lo, a->N, a->H, a->W, a->C, 1 << L.tc.bw_log2, L.tc.box_rows, promo64);
+        make_act_map(&L.tc.a_map[0][s], a->hi, a->N, a->H, a->W, a->C, L.tc.box_w, L.tc.box_rows, promo64);
+        make_act_map(&L.tc.a_map[1][s], a->lo, a->N, a->H, a->W, a->C, L.tc.box_w, L.tc.box_rows, promo64);
       }
       for (int s = L.nsrc; s < EGN_MAX_SRC; ++s) {
         L.tc.a_map[0][s] = L.tc.a_map[0][0];
