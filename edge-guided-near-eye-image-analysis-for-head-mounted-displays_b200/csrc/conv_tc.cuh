@@ -41,6 +41,7 @@ struct TcParams {
   int wide_b;                          // 1: hi*hi and hi*lo issue as ONE MMA of N = 2*n_tile against the stacked [W_hi; W_lo] tile (A_hi read once)
   int w_box;                           // 1: a W slot holds every tap of an activation box (one barrier round trip per box)
   int w_slot_taps;                     // taps per W slot (1 unless w_box)
+  int w_res;                           // 1: every (chunk, tap) weight tile of the layer stays resident in shared memory (loaded once per CTA)
   uint32_t a_plane_bytes, a_box_bytes, w_plane_bytes;
   int acc_bufs;                        // TMEM accumulator buffers (1 or 2)
   int n_aloads;
@@ -391,6 +392,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const bool ptm = p.timing != nullptr;
       long long ptm_a = 0, ptm_w = 0, ptm_c0 = 0;
       const long long ptm_start = ptm ? clock64() : 0;
+      if (p.w_res) {
+        // small layers: all weight tiles [chunk][tap] are loaded once and stay in shared memory
+        const int ntaps_all = p.g.ntaps;
+        if (dbg & 8) {
+          mbar_arrive(w_full(0));
+        } else {
+          mbar_expect_tx(w_full(0), w_tx * ntaps_all * nchunks);
+          for (int c = 0; c < nchunks; ++c)
+            for (int t = 0; t < ntaps_all; ++t) {
+              const uint32_t sW = w_base + (uint32_t)(c * ntaps_all + t) * w_tap_bytes;
+              tma_load_2d(&p.w_map[0], w_full(0), sW, c * EGN_KC, t * cout_pad);
+              if (nplanes == 2) tma_load_2d(&p.w_map[1], w_full(0), sW + w_plane, c * EGN_KC, t * cout_pad);
+            }
+        }
+      }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nb = tile % n_blocks;
         int rest = tile / n_blocks;
@@ -420,6 +436,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               if (nplanes == 2) tma_load_4d(map_lo, a_full(as), sA + a_plane, ck.c0, x0 + ld.dx, y0, nn);
             }
             if (++as == na) { as = 0; aph ^= 1u; }
+            if (p.w_res) continue;
             if (p.w_box) {
               // runs of up to w_slot_taps taps share one weight slot / barrier round trip
               for (int t0 = 0; t0 < ld.ntaps; t0 += p.w_slot_taps) {
@@ -489,6 +506,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const bool tm = p.timing != nullptr;
       long long tm_te = 0, tm_a = 0, tm_w = 0, tm_i = 0, tm_k = 0, tm_c0 = 0;
       const long long tm_start = tm ? clock64() : 0;
+      if (p.w_res) {
+        mbar_wait(w_full(0), 0u, p.err_flag, 5);
+        fence_after();
+      }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++use) {
         const int ty = (tile / (p.n_blocks * p.tiles_x)) % p.tiles_y;
         const int nsub = min(p.S, (p.g.H - ty * p.tr + p.sr - 1) / p.sr);
@@ -503,6 +524,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           constexpr int NSUB = decltype(nsub_c)::value;
           constexpr int NPL = decltype(npl_c)::value;
           constexpr int WIDE = decltype(wide_c)::value;
+          if (p.w_res) {
+            // resident weights: no weight barriers at all, every tap of a box issues in one go
+            const int n_aloads = p.n_aloads;
+            for (int c = 0; c < nchunks; ++c) {
+              for (int l = 0; l < n_aloads; ++l) {
+                const TcLoad ld = s_load[l];
+                if (tm) tm_c0 = clock64();
+                mbar_wait(a_full(as), aph, p.err_flag, 4);
+                if (tm) { const long long now = clock64(); tm_a += now - tm_c0; tm_c0 = now; }
+                fence_after();
+                const uint32_t sA = base + as * a_slot_bytes;
+                const uint32_t sW = w_base + (uint32_t)(c * ntaps + ld.tap0) * w_tap_bytes;
+                if (elect_one()) {
+                  if (!(dbg & 2)) {
+                    TcTapStep nxt = s_tap[ld.tap0];
+                    for (int j = 0; j < ld.ntaps; ++j) {
+                      const TcTapStep cur = nxt;
+                      if (j + 1 < ld.ntaps) nxt = s_tap[ld.tap0 + j + 1];
+                      const uint32_t first = (c == 0 && (cur.flags & 4u)) ? 1u : 0u;
+                      issue_tap<NSUB, NPL, WIDE>(sA + cur.a_off, a_plane, sW + j * w_tap_bytes, w_plane, d_base + cur.d_col, sub_cols, idesc, idesc_wide, first, a_sbo, a_sub16);
+                    }
+                  }
+                  if (tm) { const long long now = clock64(); tm_i += now - tm_c0; tm_c0 = now; }
+                  mma_commit(a_empty(as));
+                  if (tm) tm_k += clock64() - tm_c0;
+                }
+                __syncwarp();
+                if (++as == na) { as = 0; aph ^= 1u; }
+              }
+            }
+            return;
+          }
           if (p.w_box) {
             // one weight-barrier round trip per run of up to three taps instead of one per tap
             const int n_aloads = p.n_aloads;
@@ -985,10 +1038,20 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   if (const char* e = getenv("EGN_TC_WBOX")) p.w_box = atoi(e) ? p.w_box : 0;
   p.w_slot_taps = p.w_box ? std::min(max_box_taps, 3) : 1;
   if (budget < 2 * a_slot + 2 * w_slot * p.w_slot_taps) { p.w_box = 0; p.w_slot_taps = 1; }   // 256-wide tiles: one tap per slot
+  // small layers (32 -> 32 3x3: 36 KB, the full-resolution 1x1 layers: 8-20 KB): keep every weight tile
+  // resident instead of re-streaming it per pixel tile - frees the weight barriers and ~30 % of the
+  // TMA writes into the shared memory the MMAs read their operands from
+  p.w_res = 0;
+  {
+    const size_t all_w = w_slot * (size_t)g.ntaps * g.nchunks;
+    if (p.n_blocks == 1 && all_w <= 48 * 1024 && budget >= 2 * a_slot + all_w && !getenv("EGN_TC_NO_WRES")) {
+      p.w_res = 1; p.w_box = 1; p.w_slot_taps = g.ntaps * g.nchunks;
+    }
+  }
   const size_t w_slot_all = w_slot * p.w_slot_taps;
   p.na = 2;
-  EGN_CHECK(budget > p.na * a_slot + 2 * w_slot_all, "conv_tc: tile does not fit in shared memory");
-  p.nw = (int)std::min<size_t>(p.w_box ? 3 : 8, (budget - p.na * a_slot) / w_slot_all);
+  EGN_CHECK(budget >= p.na * a_slot + (p.w_res ? 1 : 2) * w_slot_all, "conv_tc: tile does not fit in shared memory");
+  p.nw = p.w_res ? 1 : (int)std::min<size_t>(p.w_box ? 3 : 8, (budget - p.na * a_slot) / w_slot_all);
   while (p.na < 4 && budget >= (p.na + 1) * a_slot + (size_t)p.nw * w_slot_all) ++p.na;
 }
 
