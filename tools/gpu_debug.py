@@ -129,8 +129,8 @@ if mode == "tc":
     for blk in ["enc.down_block1", "enc.down_block2", "enc.down_block3", "enc.down_block4", "enc.bottleneck"]:
         layers += [blk + "." + c for c in ("conv1", "conv21", "conv22", "conv31", "conv32", "TD.conv")]
     for u in ["dec.up_block4", "dec.up_block3", "dec.up_block2", "dec.up_block1"]:
-        layers += [u + "." + c for c in ("conv11", "conv12", "conv21", "conv22")]
-    layers += ["dec.final.conv1"]
+        layers += [u + "." + c for c in ("pre", "conv11", "conv12", "conv21", "conv22")]
+    layers += ["dec.final.conv1", "dec.final.conv2", "elReg.c1"]
     for l in layers:
         try:
             d, r = ctx.conv_selfcheck(l, 2)
