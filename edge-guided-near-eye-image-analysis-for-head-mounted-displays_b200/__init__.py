@@ -15,7 +15,7 @@ from .ritnet_v2 import DenseNet2D, getSizes                           # noqa: F4
 from .engine import Context, NET_BDCN, NET_ESF                        # noqa: F401
 from .hostapi import (calc_edge, get_predictions, evaluate_batch, MetricAccumulator,     # noqa: F401
                       preprocess_frames_u8, evaluate_ellseg_on_image, shard_frames, calc_acc,
-                      summarize_batches)
+                      summarize_batches, preprocess_frame, rescale_to_original)
 
 
 def install():

@@ -178,6 +178,64 @@ def evaluate_ellseg_on_image(frame, model, edge_model, device=None, refine=True)
     return e, s, ell[:, 1], ell[:, 0]
 
 
+def preprocess_frame(img, op_shape=(H, W), align_width=True):
+    """evaluate.py:69-104: bring a grey frame [h,w] to ``op_shape`` (width-aligned Lanczos resize, then
+    symmetric vertical zero-padding or cropping), z-score it and return ``(tensor[1,H,W] float32,
+    scale_shift)``.  Same arithmetic as the reference (numpy float64 mean / population std); the
+    reference's crop branch indexes with floats and raises on current numpy - here it crops the
+    rows the reference intended.  Frames that are already ``op_shape`` uint8 can skip this and go
+    through ``preprocess_frames_u8`` (z-score on the device)."""
+    import cv2
+    if not align_width:
+        raise SystemExit('Height alignment not implemented! Exiting ...')
+    img = np.asarray(img)
+    if op_shape[1] != img.shape[1]:
+        sc = op_shape[1] / img.shape[1]
+        width, height = int(img.shape[1] * sc), int(img.shape[0] * sc)
+        img = cv2.resize(img, (width, height), interpolation=cv2.INTER_LANCZOS4)
+        if op_shape[0] > img.shape[0]:
+            pad = op_shape[0] - img.shape[0]
+            img = np.pad(img, ((pad // 2, pad - pad // 2), (0, 0)))
+            scale_shift = (sc, pad)
+        elif op_shape[0] < img.shape[0]:
+            pad = op_shape[0] - img.shape[0]                      # negative: rows to drop
+            top = (-pad) // 2
+            img = img[top:top + op_shape[0], ...]
+            scale_shift = (sc, pad)
+        else:
+            scale_shift = (sc, 0)
+    else:
+        scale_shift = (1, 0)
+    img = (img - img.mean()) / img.std()
+    return torch.from_numpy(np.ascontiguousarray(img)).unsqueeze(0).to(torch.float32), scale_shift
+
+
+def rescale_to_original(edge_map, seg_map, pupil_ellipse, iris_ellipse, scale_shift, orig_shape):
+    """evaluate.py:168-192: map the 240x320 outputs back to the original frame - ellipse centres / axes
+    un-shifted and un-scaled (the angle is kept), maps re-padded (cropped input) or un-padded (padded
+    input) and resized with nearest neighbour."""
+    import cv2
+    pupil_ellipse = np.array(pupil_ellipse, dtype=np.float64)
+    iris_ellipse = np.array(iris_ellipse, dtype=np.float64)
+    for e in (pupil_ellipse, iris_ellipse):
+        e[1] = e[1] - np.floor(scale_shift[1] // 2)
+        e[:-1] = e[:-1] * (1 / scale_shift[0])
+    seg_map = np.asarray(seg_map)
+    edge_map = np.asarray(edge_map)
+    sh = scale_shift[1]
+    if sh < 0:
+        seg_map = np.pad(seg_map, ((-sh // 2, -sh // 2), (0, 0)))
+        edge_map = np.pad(edge_map, ((-sh // 2, -sh // 2), (0, 0)))
+    elif sh > 0:
+        # the frame had been padded by sh rows: drop them again (the reference then calls np.pad with
+        # negative widths, evaluate.py:185-188, which raises on every numpy - only the crop is kept)
+        seg_map = seg_map[sh // 2:seg_map.shape[0] - (sh - sh // 2), ...]
+        edge_map = edge_map[sh // 2:edge_map.shape[0] - (sh - sh // 2), ...]
+    seg_map = cv2.resize(seg_map, (orig_shape[1], orig_shape[0]), interpolation=cv2.INTER_NEAREST)
+    edge_map = cv2.resize(edge_map, (orig_shape[1], orig_shape[0]), interpolation=cv2.INTER_NEAREST)
+    return edge_map, seg_map, pupil_ellipse, iris_ellipse
+
+
 def shard_frames(total, rank, world):
     """Contiguous block partition of `total` frames over `world` ranks: returns
     (start, count); the first total % world ranks take one extra frame."""
