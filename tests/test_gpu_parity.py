@@ -429,3 +429,32 @@ def test_batch_of_one_shapes_and_int_id(env):
     assert loss.shape == (1,) and elOut.shape == (1, 10) and torch.isfinite(loss).all()
     gold = np.load(os.path.join(env["golden"], "fwd_baseline_edge.npz"))
     assert (egn.get_predictions(op, m).numpy()[0] == gold["pred"][0]).mean() >= 0.999
+
+
+def test_plain_c_client_matches_python_mirrors(env, tmp_path):
+    """tools/abi_client.c (gcc, no torch, device memory from the CUDA runtime) drives the same C ABI with
+    weight blobs on disk; its argmax / elPred / edge files must equal the Python mirrors' outputs bit for bit."""
+    import subprocess
+    from egn_b200.pack import pack_state_dict
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tools", "abi_client")
+    if not os.path.isfile(exe):
+        pytest.skip("tools/abi_client not built (run __graft_entry__.build())")
+    egn, dev = env["egn"], env["dev"]
+    m, st, esd = _model(env, "baseline_edge", mb=2)
+    em = egn.BDCN(); em.load_state_dict(env["bsd"]); em = em.cuda().eval(); em.micro_batch = 2
+    (tmp_path / "bdcn.blob").write_bytes(pack_state_dict(env["bsd"]))
+    (tmp_path / "esf.blob").write_bytes(pack_state_dict(esd))
+    env["img"].numpy().astype("<f4").tofile(str(tmp_path / "x.f32"))
+    r = subprocess.run([exe, str(tmp_path / "bdcn.blob"), str(tmp_path / "esf.blob"), str(tmp_path / "x.f32"), "2",
+                        str(tmp_path / "out")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    with torch.no_grad():
+        e = em.edge(env["img"].to(dev))
+        lo, eo, la, am, ep = m.infer(env["img"].to(dev), e, None)
+    got_am = np.fromfile(str(tmp_path / "out.argmax.u8"), dtype=np.uint8).reshape(2, 240, 320)
+    got_ep = np.fromfile(str(tmp_path / "out.elpred.f32"), dtype="<f4").reshape(2, 10)
+    got_e = np.fromfile(str(tmp_path / "out.edge.f32"), dtype="<f4").reshape(2, 1, 240, 320)
+    assert np.array_equal(got_e, e.cpu().numpy())
+    assert np.array_equal(got_am, am.cpu().numpy())
+    assert np.array_equal(got_ep, ep.cpu().numpy())
