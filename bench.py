@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("EGN_MICRO_BATCH", "256")))
     ap.add_argument("--config", default="baseline_edge")
-    ap.add_argument("--cpu-frames", type=int, default=8)
+    ap.add_argument("--cpu-frames", type=int, default=32, help="frames per CPU step (bounded sample of the workload: ~8 s per step on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layer-table", default=None, help="write the per-layer kernel-time CSV of the timed region here")
     args = ap.parse_args()
