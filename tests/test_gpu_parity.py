@@ -458,3 +458,33 @@ def test_plain_c_client_matches_python_mirrors(env, tmp_path):
     assert np.array_equal(got_e, e.cpu().numpy())
     assert np.array_equal(got_am, am.cpu().numpy())
     assert np.array_equal(got_ep, ep.cpu().numpy())
+
+
+def test_full_size_batch_properties(env):
+    """BASELINE.json's batch of 256 frames (too large for the CPU oracle) through size-independent
+    properties: frames are independent, so a frame must produce the same segmentation / centres /
+    ellipse parameters wherever it sits in the batch and in whichever micro-batch it lands, and the
+    metric accumulators of the whole batch must equal the sum of those of its halves."""
+    egn, synth, dev = env["egn"], env["synth"], env["dev"]
+    m, st, esd = _model(env, "baseline_edge", mb=64)
+    em = egn.BDCN(); em.load_state_dict(env["bsd"]); em = em.cuda().eval(); em.micro_batch = 64
+    half = synth.randn_frames(128, seed=7)
+    x = torch.cat([half, half.flip(0)], 0).to(dev)               # frame i == frame 255 - i
+    lab = synth.evaluate_style_labels(256).to(torch.uint8).to(dev)
+    cond = torch.zeros(256, 4, device=dev)
+    c = torch.full((256, 2), 100.0, device=dev)
+    with torch.no_grad():
+        e = em.edge(x)
+        lo, eo, la, am, ep = m.infer(x, e, cond)
+    assert torch.isfinite(lo).all() and torch.isfinite(eo).all()
+    assert (am[:128] == am[128:].flip(0)).float().mean().item() >= 0.99999
+    np.testing.assert_allclose(ep[:128].cpu().numpy(), ep[128:].flip(0).cpu().numpy(), atol=1e-4)
+    np.testing.assert_allclose(eo[:128].cpu().numpy(), eo[128:].flip(0).cpu().numpy(), atol=1e-4)
+    np.testing.assert_allclose(e[:128].cpu().numpy(), e[128:].flip(0).cpu().numpy(), atol=1e-6)
+    ctx = m.context(dev)
+    whole, a, b = egn.MetricAccumulator(dev), egn.MetricAccumulator(dev), egn.MetricAccumulator(dev)
+    ctx.metrics_accumulate(am, lab, cond, whole.acc, c, c, eo, ep)
+    ctx.metrics_accumulate(am[:128].contiguous(), lab[:128].contiguous(), cond[:128], a.acc, c[:128], c[:128], eo[:128].contiguous(), ep[:128].contiguous())
+    ctx.metrics_accumulate(am[128:].contiguous(), lab[128:].contiguous(), cond[128:], b.acc, c[128:], c[128:], eo[128:].contiguous(), ep[128:].contiguous())
+    np.testing.assert_allclose(whole.acc.cpu().numpy(), (a.acc + b.acc).cpu().numpy(), rtol=1e-12)
+    assert whole.result()["frames"] == 256
