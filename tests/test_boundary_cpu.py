@@ -204,3 +204,22 @@ def test_summarize_batches_matches_calc_acc_aggregation():
         warnings.simplefilter("ignore", category=RuntimeWarning)
         np.testing.assert_allclose(ious, np.nanmean(np.stack(iou_b), 0), rtol=1e-12)
         np.testing.assert_allclose([pl, il, ps, isg], np.nanmean(np.stack(dist_b), 0), rtol=1e-12)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/egn.h must be consumable by a C compiler (no C++ / torch types in the ABI), and the
+    plain-C client of the whole path must compile against it."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "t.c"
+    src.write_text('#include "egn.h"\nint main(void) { egn_config c = {0, 0, 0, 0, 0, 8}; (void)c; return egn_version() < 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I" + os.path.join(root, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if os.path.isdir("/usr/local/cuda/include"):
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-fsyntax-only", "-I" + os.path.join(root, "include"),
+                            "-I/usr/local/cuda/include", os.path.join(root, "tools", "abi_client.c")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
