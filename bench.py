@@ -8,6 +8,16 @@ Workload (BASELINE.json configs[1]): configs/baseline_edge.yaml, batch 256 per G
 240x320 frames (seeded z-scored noise), synthetic checkpoints (oracle/synth.py).
 One step = calc_edge + DenseNet2D forward + argmax / soft-argmax centres + metric accumulation for
 one batch.  Prints ONE JSON line (rank 0).
+
+    python bench.py --config baseline_adain_edge ...         # BASELINE.json configs[2]
+    python bench.py --stream 8 --steps 200                   # configs[3]: evaluate.py's streaming path at batch 8
+                                                             # (u8 ingest -> edge -> ESF-Net -> argmax -> ellipse fit
+                                                             #  -> D2H), latency p50 / p99 in the same JSON schema
+
+The batch carries PLANTED frames (tests/golden/planted_<config>.npz: the reference's own outputs for two
+golden frames and eight real eye crops, at batch positions 0 / 127 / 255 and spread through the batch);
+after the timed region their argmax agreement, centre error and ellipse-parameter error go into the JSON
+line ("parity"), so the benchmarked configuration itself (micro-batch, tiling) is pinned to the reference.
 """
 import argparse
 import json
@@ -84,12 +94,80 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def cpu_reference_fps(frames, repeats, threads):
+
+PLANTED_CONFIGS = ("baseline_edge", "baseline_adain_edge")
+
+
+def planted_frames():
+    """The ten frames of oracle/make_golden_planted.py (same construction; fixtures only, no oracle code)."""
+    import numpy as np
+    gd = os.path.join(ROOT, "tests", "golden")
+    img = np.load(os.path.join(gd, "fwd_input.npz"))["img"]
+    fr = np.load(os.path.join(gd, "frames_u8.npz"))["frames"][:8].astype(np.float64)
+    z = np.stack([((f - f.mean()) / f.std()).astype(np.float32)[None] for f in fr])
+    return np.concatenate([img, z], 0)
+
+
+def planted_positions(B):
+    """[(batch position, planted index)]: golden frame 0 at 0 and B-1, golden frame 1 at B/2-1, the eight real
+    crops spread through the batch."""
+    if B < 16:
+        return []
+    pos = [(0, 0), (B // 2 - 1, 1), (B - 1, 0)]
+    pos += [(int((k + 0.5) * B / 8), 2 + k) for k in range(8)]
+    return pos
+
+
+def plant(x_host, B):
+    import torch
+    pos = planted_positions(B)
+    if pos:
+        pf = torch.from_numpy(planted_frames())
+        for p, i in pos:
+            x_host[p] = pf[i]
+    return pos
+
+
+def planted_parity(config, pos, argmax, el_pred, el_out):
+    """Planted frames of the batch against the reference's outputs (north_star bars: >= 99.9 % argmax
+    agreement, centres within 0.25 px, ellipse parameters within 1e-2 relative with floor 1e-2)."""
+    import numpy as np
+    path = os.path.join(ROOT, "tests", "golden", "planted_%s.npz" % config)
+    if not pos or not os.path.isfile(path):
+        return None
+    g = np.load(path)
+    am = argmax.cpu().numpy()
+    ep, eo = el_pred.cpu().numpy().astype(np.float64), el_out.cpu().numpy().astype(np.float64)
+    scale = np.array([160.0, 120.0])
+    agree, centre, ell = 1.0, 0.0, 0.0
+    par = [2, 3, 4, 7, 8, 9]
+    for p, i in pos:
+        agree = min(agree, float((am[p] == g["pred"][i]).mean()))
+        for sl in (slice(0, 2), slice(5, 7)):
+            centre = max(centre, float(np.abs((ep[p, sl] - g["elPred"][i, sl]) * scale).max()),
+                         float(np.abs((eo[p, sl] - g["elOut"][i, sl]) * scale).max()))
+        for got, want in ((ep[p, par], g["elPred"][i, par]), (eo[p, par], g["elOut"][i, par])):
+            ell = max(ell, float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-2))))
+    ok = agree >= 0.999 and centre < 0.25 and ell < 1e-2
+    return {"planted_frames": len(pos), "positions": [p for p, _ in pos], "argmax_agreement": agree,
+            "centre_px": centre, "ell_rel": ell, "pass": bool(ok),
+            "against": "tests/golden/planted_%s.npz (outputs of the unmodified reference, oracle/make_golden_planted.py)" % config}
+
+
+def dtype_label(info):
+    if not info["tensor_core_path"]:
+        return "f32-simt (EGN_CONV=simt debugging path: NOT the benchmarked engine)"
+    if info["products_per_mac"] == 3:
+        return "bf16x3 (split-bf16 operands: hi*hi + lo*hi + hi*lo tcgen05 products per MAC, fp32 accumulate)"
+    return "bf16x%d (EGN_NSPLIT=%d: does NOT meet the parity bars)" % (info["products_per_mac"], info["products_per_mac"])
+
+
+def cpu_reference_fps(frames, repeats, threads, config="baseline_edge"):
     """The CPU arm: oracle/graph.py (torch fp32 port of the reference path) on host cores."""
     import torch
     from oracle import graph, synth
     torch.set_num_threads(threads)
-    st = synth.SETTINGS["baseline_edge"]
+    st = synth.SETTINGS[config]
     bsd, esd = synth.make_bdcn_state(0), synth.make_esf_state(st, 0)
     img = synth.randn_frames(frames, seed=1)
     best = None
@@ -108,19 +186,25 @@ def workload_config(config, batch, world, micro_batch):
     return {"workload": "%s.yaml: BDCN edge extractor + ESF-Net, batch %d per GPU, 240x320" % (config, batch),
             "global_batch": batch * world, "micro_batch": micro_batch,
             "parallelism": "dp%d (batch-sharded frames)" % world,
-            "cache": "working set per step (%.1f GB activations) exceeds the 126 MB L2; no flush needed" % (micro_batch * 0.4),
+            "cache": "activations written and re-read by each step (tens of GB at this micro-batch) exceed the 126 MB L2; no flush needed",
             "weights": "synthetic seeded checkpoints in the reference container formats"}
 
 
-def conv_traffic():
-    """Per-launch DRAM traffic of conv_tc_kernel from the committed ncu capture (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
-    if os.path.isfile(p):
+def conv_traffic(config, micro_batch):
+    """Per-launch DRAM traffic of conv_tc_kernel from the newest committed ncu capture (profiles/): a capture
+    taken at this micro-batch and configuration is used as is, anything else is scaled and SAYS so."""
+    import glob
+    best = None
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_conv_traffic*.json"))):
         try:
-            return json.load(open(p))
+            d = json.load(open(p))
         except Exception:
-            return None
-    return None
+            continue
+        d["file"] = os.path.basename(p)
+        exact = int(d.get("frames", 16)) == micro_batch and d.get("config", "baseline_edge") == config
+        if best is None or exact or not best[0]:
+            best = (exact, d)
+    return best
 
 
 def run_reference(args):
@@ -132,7 +216,7 @@ def run_reference(args):
     frames = args.cpu_frames
     from oracle import graph, synth
     torch.set_num_threads(threads)
-    st = synth.SETTINGS["baseline_edge"]
+    st = synth.SETTINGS[args.config]
     bsd, esd = synth.make_bdcn_state(0), synth.make_esf_state(st, 0)
     img = synth.randn_frames(frames, seed=1)
 
@@ -160,6 +244,93 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_stream(args):
+    """BASELINE.json configs[3]: evaluate.py's per-frame video path (evaluate.py:235-285) at `--stream` frames
+    per call: uint8 frames on the host -> H2D -> z-score ingest -> BDCN edge -> ESF-Net -> argmax / centres ->
+    both ellipses refined -> D2H of edge map, segmentation and ellipses.  One step = one such call; `value`
+    is frames/s with the call's inputs resident on the device, `e2e` the same from pinned host memory to
+    host results; latency percentiles of the e2e call are reported beside them."""
+    import numpy as np
+    import torch
+    import egn_b200
+    from oracle import synth           # synthetic checkpoints only (test infrastructure)
+    assert args.gpus == 1, "the streaming configuration is a single-GPU latency measurement"
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    B = args.stream
+    st = synth.SETTINGS[args.config]
+    edge_model = egn_b200.BDCN(); edge_model.load_state_dict(synth.make_bdcn_state(0))
+    model = egn_b200.DenseNet2D(st); model.load_state_dict(synth.make_esf_state(st, 0))
+    edge_model = edge_model.to(dev).eval(); model = model.to(dev).eval()
+    edge_model.micro_batch = model.micro_batch = B
+    fr = np.load(os.path.join(ROOT, "tests", "golden", "frames_u8.npz"))["frames"]
+    frames = torch.from_numpy(np.stack([fr[i % len(fr)] for i in range(B)])).pin_memory()
+    frames_dev = frames.to(dev)
+    h_edge = torch.empty((B, 1, 240, 320), dtype=torch.float32).pin_memory()
+    h_seg = torch.empty((B, 240, 320), dtype=torch.uint8).pin_memory()
+    h_ell = torch.empty((B, 2, 5), dtype=torch.float64).pin_memory()
+    ctx = None
+
+    def call(src):
+        x = egn_b200.preprocess_frames_u8(src, dev)
+        edge = edge_model.edge(x)
+        logits, el_out, latent, argmax, el_pred = model.infer(x, edge, None)
+        ell = model.context(dev).ellipse_refine(argmax, el_pred, True)
+        return edge, argmax, ell
+
+    def step_resident():
+        call(frames_dev)
+
+    def step_e2e():
+        edge, argmax, ell = call(frames.to(dev, non_blocking=True))
+        h_edge.copy_(edge, non_blocking=True); h_seg.copy_(argmax, non_blocking=True); h_ell.copy_(ell, non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    with torch.no_grad():
+        for _ in range(max(3, args.warmup)):
+            step_e2e()
+        ectx, mctx = edge_model.context(dev), model.context(dev)
+        l0 = ectx.launch_count() + mctx.launch_count()
+        sampler = ClockSampler(0); sampler.start()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step_resident()
+        e1.record(); torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        launches = ectx.launch_count() + mctx.launch_count() - l0
+        lat = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            step_e2e()
+            lat.append((time.perf_counter() - t0) * 1e3)
+        sampler.stop_flag = True
+        info = mctx.info()
+    lat.sort()
+    pct = lambda q: lat[min(len(lat) - 1, int(q * len(lat)))]
+    ms_e2e = sum(lat)
+    gf = GFLOP_PER_FRAME.get(args.config)
+    peak_tf, peak_gbs, peak_src = read_peaks()
+    fps = B * args.steps / (ms / 1e3)
+    line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": dtype_label(info), "data": "real eye crops (tests/golden/frames_u8.npz, videos/example1.avi) tiled to the batch; synthetic weights",
+            "config": {"workload": "evaluate.py video path (%s.yaml): streaming 240x320 frames at batch %d, latency plus ellipse fit, 1 B200"
+                                   % (args.config, B), "global_batch": B, "micro_batch": B, "parallelism": "dp1",
+                       "cache": "latency measurement: one small call per step, L2-resident by nature (that is the workload)"},
+            "latency_ms": {"p50": pct(0.5), "p99": pct(0.99), "mean": ms_e2e / len(lat), "calls": len(lat),
+                           "what": "host u8 frames -> edge map, segmentation and both refined ellipses on the host, per call"},
+            "e2e": {"value": B * len(lat) / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": int(frames.numel()),
+                    "d2h_bytes_per_step": int(h_edge.numel() * 4 + h_seg.numel() + h_ell.numel() * 8), "ms_per_step": ms_e2e / len(lat)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "whole call (latency-bound at this batch)", "achieved": fps * gf / 1000.0 if gf else None,
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": fps * gf / 1000.0 / peak_tf if gf else None, "peak_source": peak_src,
+                         "traffic": None},
+            "clocks": sampler.summary()}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -172,9 +343,13 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=32, help="frames per CPU step (bounded sample of the workload: ~8 s per step on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layer-table", default=None, help="write the per-layer kernel-time CSV of the timed region here")
+    ap.add_argument("--stream", type=int, default=0, help="streaming mode (evaluate.py video path): frames per call, e.g. 1 / 8 / 32")
+    ap.add_argument("--allow-nonparity", action="store_true", help="accept EGN_NSPLIT / EGN_CONV knobs that fail the parity bars (the line is labelled)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.stream:
+        return run_stream(args)
 
     import numpy as np
     import torch
@@ -211,7 +386,9 @@ def main():
     edge_model.micro_batch = model.micro_batch = args.micro_batch
     B = args.batch
     # weak scaling: every rank owns its own B frames (frames shard by batch, no data-path collective)
-    x_host = synth.randn_frames(B, seed=100 + rank).pin_memory()
+    x_host = synth.randn_frames(B, seed=100 + rank)
+    planted = plant(x_host, B) if args.config in PLANTED_CONFIGS else []
+    x_host = x_host.pin_memory()
     lab_host = synth.evaluate_style_labels(B).to(torch.uint8).pin_memory()
     x_dev = x_host.to(dev)
     lab_dev = lab_host.to(dev)
@@ -253,10 +430,15 @@ def main():
             fn()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        mine = float(e0.elapsed_time(e1))
+        per_rank = [mine]
         if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+            allms = torch.zeros(world, device=dev, dtype=torch.float64)
+            allms[rank] = mine
+            dist.all_reduce(allms, op=dist.ReduceOp.SUM)
+            per_rank = [float(v) for v in allms.tolist()]
+        timed.per_rank = per_rank
+        return max(per_rank)
 
     with torch.no_grad():
         for _ in range(args.warmup):
@@ -269,6 +451,7 @@ def main():
         if rank == 0:
             sampler.start()
         ms = timed(step_resident, args.steps)
+        rank_ms = [v / args.steps for v in timed.per_rank]
         acc.all_reduce()
         sampler.stop_flag = True
         launches = ectx.launch_count() + mctx.launch_count() - l0
@@ -281,6 +464,15 @@ def main():
         for _ in range(2):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
+        # the planted frames of the LAST end-to-end step (host results of the public call path)
+        parity = planted_parity(args.config, planted, out_am, out_el, out_eo)
+        info = mctx.info()
+        einfo = ectx.info()
+    if (info["products_per_mac"] != 3 or not info["tensor_core_path"] or einfo["products_per_mac"] != 3
+            or not einfo["tensor_core_path"]) and not args.allow_nonparity:
+        raise SystemExit("bench.py: the engine runs with EGN_NSPLIT=%d / tensor_core_path=%d, which is not the parity "
+                         "configuration; pass --allow-nonparity to time it anyway (the line is labelled)"
+                         % (info["products_per_mac"], info["tensor_core_path"]))
 
     fps = world * B * args.steps / (ms / 1000.0)
     fps_e2e = world * B * args.steps / (ms_e2e / 1000.0)
@@ -288,11 +480,13 @@ def main():
     peak_tf, peak_gbs, peak_src = read_peaks()
     achieved = conv_flops / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
     gf = GFLOP_PER_FRAME.get(args.config)
-    traffic = conv_traffic()
+    tr = conv_traffic(args.config, min(args.micro_batch, B))
+    traffic = tr[1] if tr else None
+    products = info["products_per_mac"]
     if rank == 0:
         line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)", "data": "synthetic",
+                "vs_baseline": None, "dtype": dtype_label(info), "data": "synthetic",
                 "config": workload_config(args.config, B, world, args.micro_batch),
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
                         "d2h_bytes_per_step": int(out_am.numel() + 4 * (out_el.numel() + out_eo.numel() + out_lat.numel())),
@@ -301,10 +495,15 @@ def main():
                 "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (all %d conv launches of the timed region)" % conv_n,
                              "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                              "peak_source": peak_src,
-                             # the capture ran 16-frame launches; a launch of this run carries micro_batch frames
+                             # every algorithmic MAC costs `products` bf16 tensor-core products, so
+                             # frac can never exceed 1/products; the second figure is the fraction of THAT ceiling
+                             "products_per_mac": products, "policy_ceiling_frac": 1.0 / products,
+                             "frac_of_policy_ceiling": achieved / peak_tf * products,
                              "traffic": ((traffic["dram_bytes_per_launch"] * min(args.micro_batch, B) / float(traffic.get("frames", 16)))
                                          if traffic else None),
-                             "traffic_note": ((traffic["note"] + "; scaled here to %d-frame launches" % min(args.micro_batch, B))
+                             "traffic_note": ((traffic["note"] + (" [%s]" % traffic["file"]) +
+                                               ("" if tr[0] else "; EXTRAPOLATED: scaled from that capture to %d-frame launches of %s"
+                                                % (min(args.micro_batch, B), args.config)))
                                               if traffic else "no ncu capture committed yet"),
                              "algorithmic_flops_per_launch": conv_flops / conv_n if conv_n else None,
                              "ms_per_launch": conv_ms / conv_n if conv_n else None,
@@ -313,10 +512,14 @@ def main():
                              "whole_step_frac": fps / world * gf / 1000.0 / peak_tf if gf else None},
                 "clocks": sampler.summary(),
                 "hbm_used_gb": round((torch.cuda.mem_get_info(dev)[1] - torch.cuda.mem_get_info(dev)[0]) / 1e9, 1),
-                "metrics_check": acc.result()["frames"]}
+                "metrics_check": acc.result()["frames"], "parity": parity,
+                "rank_ms_per_step": rank_ms,
+                "workspace_gb": round((info["workspace_bytes"] + einfo["workspace_bytes"]) / 1e9, 2)}
+        if gf:
+            line["roofline"]["whole_step_frac_of_policy_ceiling"] = fps / world * gf / 1000.0 / peak_tf * products
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            cfps, csec = cpu_reference_fps(args.cpu_frames, 2, threads)
+            cfps, csec = cpu_reference_fps(args.cpu_frames, 2, threads, args.config)
             line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": threads, "kind": "port",
                                     "sample": "best of 2 x %d frames (%.1f s each), oracle/graph.py torch-fp32 port of "
                                               "calc_edge + DenseNet2D forward + get_predictions" % (args.cpu_frames, csec)}

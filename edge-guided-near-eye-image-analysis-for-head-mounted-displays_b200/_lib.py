@@ -7,13 +7,19 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libegn.so")
 
 
+class EgnInfo(ctypes.Structure):
+    _fields_ = [("device", ctypes.c_int), ("num_sms", ctypes.c_int), ("micro_batch", ctypes.c_int),
+                ("products_per_mac", ctypes.c_int), ("tensor_core_path", ctypes.c_int),
+                ("workspace_bytes", ctypes.c_longlong)]
+
+
 class EgnConfig(ctypes.Structure):
     _fields_ = [("add_edge", ctypes.c_int), ("add_seg", ctypes.c_int), ("seg_detach", ctypes.c_int),
                 ("input_concat", ctypes.c_int), ("only_edge", ctypes.c_int), ("style_dim", ctypes.c_int)]
 
 
 EXPORTS = ["egn_last_error", "egn_version", "egn_create", "egn_destroy", "egn_set_weights", "egn_plan",
-           "egn_bdcn_forward", "egn_esf_forward", "egn_seg_post", "egn_metrics_accumulate",
+           "egn_bdcn_forward", "egn_bdcn_forward_all", "egn_info", "egn_esf_forward", "egn_seg_post", "egn_metrics_accumulate",
            "egn_ellipse_refine", "egn_preprocess_u8", "egn_forward_loss", "egn_launch_count", "egn_flops_per_frame", "egn_debug_read",
            "egn_conv_selfcheck", "egn_profile", "egn_profile_read", "egn_profile_table"]
 
@@ -41,6 +47,8 @@ def load():
     lib.egn_set_weights.argtypes = [vp, ci, vp, ctypes.c_size_t]
     lib.egn_plan.argtypes = [vp, ci]
     lib.egn_bdcn_forward.argtypes = [vp, vp, ci, vp, ci, vp]
+    lib.egn_bdcn_forward_all.argtypes = [vp, vp, ci, vp, vp, ci, vp]
+    lib.egn_info.argtypes = [vp, ctypes.POINTER(EgnInfo)]
     lib.egn_esf_forward.argtypes = [vp, vp, vp, vp, vp, vp, ci, vp]
     lib.egn_seg_post.argtypes = [vp, vp, vp, vp, vp, vp, ci, vp]
     lib.egn_metrics_accumulate.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, ci, vp]

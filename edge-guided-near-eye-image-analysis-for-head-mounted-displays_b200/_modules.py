@@ -41,15 +41,28 @@ class ParamTree(nn.Module):
 
 class EngineBound(ParamTree):
     """Binds the module's current tensors to a device context on first use and re-binds when they
-    change (load_state_dict / in-place edits bump tensor versions) or the module moves."""
+    change (load_state_dict / in-place edits bump tensor versions) or the module moves.
+
+    Contexts are cached PER DEVICE on the module that owns the parameters.  ``nn.DataParallel``
+    (test.py:264-269,296 wraps the model whenever more than one GPU is visible) replicates the module on
+    every forward; a replica never owns a context - it resolves to its primary's cache entry for the
+    device it was scattered to, which is created once from the primary's tensors and reused by later
+    forwards.  A module only ever closes contexts it created itself."""
     _net = None
     _setting = None
 
     def _init_binding(self):
-        self._ctx = None
-        self._bound_key = None
+        self._ctxs = {}            # device -> (Context, key)
         self._items = None
+        self._primary = None       # set on DataParallel replicas
         self.micro_batch = None
+
+    def _replicate_for_data_parallel(self):
+        replica = super()._replicate_for_data_parallel()
+        replica._primary = self._primary if self._primary is not None else self
+        replica._ctxs = None       # replicas own nothing
+        replica._items = None
+        return replica
 
     def _apply(self, fn, *a, **k):
         # .to()/.cuda()/.float() may replace buffer tensors: drop the cached tensor list
@@ -65,17 +78,24 @@ class EngineBound(ParamTree):
         return self._items
 
     def _ensure_ctx(self, device):
-        items = self._tensors()
-        key = (device, self.micro_batch, tuple([(t._version, t.data_ptr()) for _, t in items]))
-        if self._ctx is None or key != self._bound_key:
-            if self._ctx is not None:
-                self._ctx.close()
-            ctx = Context(device, self._setting, self.micro_batch)
-            ctx.set_weights(self._net, {k: t for k, t in items})
-            self._ctx, self._bound_key = ctx, key
-        return self._ctx
+        owner = self._primary if self._primary is not None else self
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        items = owner._tensors()
+        key = (owner.micro_batch, tuple([(t._version, t.data_ptr()) for _, t in items]))
+        hit = owner._ctxs.get(device)
+        if hit is None or hit[1] != key:
+            if hit is not None:
+                hit[0].close()
+            ctx = Context(device, owner._setting, owner.micro_batch)
+            ctx.set_weights(owner._net, {k: t for k, t in items})
+            owner._ctxs[device] = (ctx, key)
+            return ctx
+        return hit[0]
 
     def context(self, device=None):
         if device is None:
-            device = next(self.parameters()).device
+            owner = self._primary if self._primary is not None else self
+            device = next(owner.parameters()).device
         return self._ensure_ctx(torch.device(device))

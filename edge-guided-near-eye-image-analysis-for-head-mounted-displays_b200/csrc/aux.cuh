@@ -250,6 +250,10 @@ struct BdcnTailParams {
   int K[5], stride[5], crop[5];
   float alpha[5], beta[5], cA[5], cB[5], fuse_bias;
   float* out;              // [N][H][W]
+  // optional: the ten per-scale sigmoids BDCN.forward returns before the fused map (bdcn_new.py:163-191),
+  // side + k * side_stride -> [N][H][W] for k = p1_1..p5_1, p1_2..p5_2; nullptr skips them (only [-1] is consumed)
+  float* side;
+  long long side_stride;
   int N, H, W;
 };
 
@@ -262,6 +266,8 @@ __global__ void bdcn_tail_kernel(const BdcnTailParams p) {
   const int n = (int)(pix / ((long long)p.W * p.H));
   const float2 s1 = reinterpret_cast<const float2*>(p.score[0])[pix];
   float acc = p.fuse_bias + p.alpha[0] * (s1.x + p.cA[0]) + p.beta[0] * (s1.y + p.cB[0]);
+  float u[5], v[5];          // upsampled + cropped s_k / s_k1 at this pixel (used by the side outputs only)
+  u[0] = s1.x + p.cA[0]; v[0] = s1.y + p.cB[0];
 #pragma unroll
   for (int k = 1; k < 5; ++k) {
     const int st = p.stride[k], K = p.K[k];
@@ -284,8 +290,20 @@ __global__ void bdcn_tail_kernel(const BdcnTailParams p) {
       }
     }
     acc += p.alpha[k] * ua + p.beta[k] * ub;
+    u[k] = ua; v[k] = ub;
   }
   p.out[pix] = 1.f / (1.f + __expf(-acc));
+  if (p.side) {
+    // p_k_1 = s_k + o_{k-1} + ... + o_1 ; p_k_2 = s_k1 + o_{k+1,1} + ... + o_51   (bdcn_new.py:165-174)
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      a += u[k];
+      b += v[4 - k];
+      p.side[(long long)k * p.side_stride + pix] = 1.f / (1.f + __expf(-a));
+      p.side[(long long)(9 - k) * p.side_stride + pix] = 1.f / (1.f + __expf(-b));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------

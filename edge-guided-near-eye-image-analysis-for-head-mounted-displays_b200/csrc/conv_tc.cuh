@@ -1055,13 +1055,15 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   while (p.na < 4 && budget >= (p.na + 1) * a_slot + (size_t)p.nw * w_slot_all) ++p.na;
 }
 
+// The dynamic shared-memory opt-in is a per-DEVICE function attribute: egn_create calls this with the
+// context's device current, so every device that owns a context has it (a process-wide flag would leave
+// the second GPU of a single process without it).
+static void tc_prepare_device() {
+  CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+}
+
 static void tc_launch(const TcParams& p, int num_sms, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   const size_t smem = tc_smem_bytes(p);
   EGN_CHECK(smem <= 227 * 1024, "conv_tc smem budget exceeded");
   int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;

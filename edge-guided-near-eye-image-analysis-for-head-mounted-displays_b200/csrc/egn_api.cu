@@ -15,6 +15,17 @@ struct egn_ctx {
 
 static thread_local std::string g_err;
 
+// Every entry point runs with the context's device current and puts the caller's device back on exit
+// (torch's notion of the current device must not change under the caller).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) CUDA_OK(cudaSetDevice(dev)); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 #define API_BEGIN try {
 #define API_END                                   \
   }                                               \
@@ -31,7 +42,7 @@ static thread_local std::string g_err;
 extern "C" {
 
 const char* egn_last_error(void) { return g_err.c_str(); }
-int egn_version(void) { return 100; }
+int egn_version(void) { return 200; }
 
 int egn_create(int device, const egn_config* cfg, egn_ctx** out) {
   API_BEGIN
@@ -40,7 +51,7 @@ int egn_create(int device, const egn_config* cfg, egn_ctx** out) {
   cudaError_t e = cudaGetDeviceCount(&ndev);
   EGN_CHECK(e == cudaSuccess && ndev > 0, std::string("no CUDA device: ") + cudaGetErrorString(e));
   EGN_CHECK(device >= 0 && device < ndev, "bad device index");
-  CUDA_OK(cudaSetDevice(device));
+  DeviceGuard guard(device);
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, device));
   EGN_CHECK(prop.major == 10, "libegn.so is built for sm_100a (B200) only; found sm_" +
@@ -57,6 +68,7 @@ int egn_create(int device, const egn_config* cfg, egn_ctx** out) {
   c->eng.nsplit = ns ? atoi(ns) : 3;
   EGN_CHECK(c->eng.nsplit == 1 || c->eng.nsplit == 3, "EGN_NSPLIT must be 1 or 3");
   c->eng.err_flag = (int*)c->eng.mem_misc.alloc(sizeof(int));
+  Engine::prepare_device();
   if (const char* fg = getenv("EGN_L2_FETCH")) {      // tuning knob: L2 fetch granularity hint (32 / 64 / 128 bytes)
     CUDA_OK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg)));
   }
@@ -67,7 +79,7 @@ int egn_create(int device, const egn_config* cfg, egn_ctx** out) {
 int egn_destroy(egn_ctx* ctx) {
   API_BEGIN
   if (ctx) {
-    cudaSetDevice(ctx->eng.device);
+    DeviceGuard guard(ctx->eng.device);
     cudaDeviceSynchronize();
     delete ctx;
   }
@@ -77,7 +89,7 @@ int egn_destroy(egn_ctx* ctx) {
 int egn_set_weights(egn_ctx* ctx, int net, const void* blob, size_t bytes) {
   API_BEGIN
   EGN_CHECK(ctx && blob, "null argument");
-  CUDA_OK(cudaSetDevice(ctx->eng.device));
+  DeviceGuard guard(ctx->eng.device);
   if (net == EGN_NET_BDCN) {
     EGN_CHECK(!ctx->eng.built_bdcn, "BDCN weights already bound; create a new context to reload");
     ctx->eng.sd_bdcn = parse_blob(blob, bytes);
@@ -105,8 +117,28 @@ int egn_bdcn_forward(egn_ctx* ctx, const float* x, int planes, float* edge_out, 
   API_BEGIN
   EGN_CHECK(ctx && x && edge_out && batch > 0, "bad argument");
   EGN_CHECK(planes == 1 || planes == 3, "planes must be 1 (grey, replicated by the caller's cat) or 3");
-  CUDA_OK(cudaSetDevice(ctx->eng.device));
+  DeviceGuard guard(ctx->eng.device);
   ctx->eng.bdcn_forward(x, planes, edge_out, batch, (cudaStream_t)stream);
+  API_END
+}
+
+int egn_bdcn_forward_all(egn_ctx* ctx, const float* x, int planes, float* edge_out, float* side_out, int batch,
+                         void* stream) {
+  API_BEGIN
+  EGN_CHECK(ctx && x && edge_out && side_out && batch > 0, "bad argument");
+  EGN_CHECK(planes == 1 || planes == 3, "planes must be 1 (grey, replicated by the caller's cat) or 3");
+  DeviceGuard guard(ctx->eng.device);
+  ctx->eng.bdcn_forward(x, planes, edge_out, batch, (cudaStream_t)stream, side_out);
+  API_END
+}
+
+int egn_info(egn_ctx* ctx, egn_info_t* out) {
+  API_BEGIN
+  EGN_CHECK(ctx && out, "null argument");
+  const Engine& e = ctx->eng;
+  out->device = e.device; out->num_sms = e.num_sms; out->micro_batch = e.mb;
+  out->products_per_mac = e.nsplit; out->tensor_core_path = e.use_tc ? 1 : 0;
+  out->workspace_bytes = (long long)(e.mem_bdcn.total + e.mem_esf.total + e.mem_misc.total);
   API_END
 }
 
@@ -114,7 +146,7 @@ int egn_esf_forward(egn_ctx* ctx, const float* x, const float* edge, float* logi
                     float* latent, int batch, void* stream) {
   API_BEGIN
   EGN_CHECK(ctx && x && logits && el_out && latent && batch > 0, "bad argument");
-  CUDA_OK(cudaSetDevice(ctx->eng.device));
+  DeviceGuard guard(ctx->eng.device);
   ctx->eng.esf_forward(x, edge, logits, el_out, latent, batch, (cudaStream_t)stream);
   API_END
 }
@@ -123,7 +155,7 @@ int egn_seg_post(egn_ctx* ctx, const float* logits, const float* el_out, const f
                  uint8_t* argmax_u8, float* el_pred, int batch, void* stream) {
   API_BEGIN
   EGN_CHECK(ctx && logits && el_out && argmax_u8 && el_pred && batch > 0, "bad argument");
-  CUDA_OK(cudaSetDevice(ctx->eng.device));
+  DeviceGuard guard(ctx->eng.device);
   cudaStream_t st = (cudaStream_t)stream;
   if (ctx->partial_cap < batch) {
     ctx->partial = (float*)ctx->eng.mem_misc.alloc((size_t)batch * POST_SLICES * 8 * sizeof(float));
@@ -146,7 +178,7 @@ int egn_metrics_accumulate(egn_ctx* ctx, const uint8_t* argmax_u8, const void* l
   EGN_CHECK(ctx && argmax_u8 && labels && cond && acc && batch > 0, "bad argument");
   EGN_CHECK((pupil_c == nullptr) == (iris_c == nullptr), "pupil_c and iris_c must be given together");
   EGN_CHECK(!pupil_c || (el_out && el_pred), "centres need el_out and el_pred");
-  CUDA_OK(cudaSetDevice(ctx->eng.device));
+  DeviceGuard guard(ctx->eng.device);
   cudaStream_t st = (cudaStream_t)stream;
   if (ctx->counts_cap < batch) {
     ctx->counts = (int*)ctx->eng.mem_misc.alloc((size_t)batch * 9 * sizeof(int));
@@ -170,7 +202,7 @@ int egn_forward_loss(egn_ctx* ctx, const float* logits, const void* target, int 
   API_BEGIN
   EGN_CHECK(ctx && logits && target && spat_w && dist_map && cond && pupil_c && el_norm && el_out && el_pred && loss &&
                 batch > 0, "bad argument");
-  CUDA_OK(cudaSetDevice(ctx->eng.device));
+  DeviceGuard guard(ctx->eng.device);
   cudaStream_t st = (cudaStream_t)stream;
   if (ctx->loss_cap < batch) {
     ctx->loss_partial = (double*)ctx->eng.mem_misc.alloc((size_t)batch * LOSS_SLICES * LOSS_TERMS * sizeof(double));
@@ -190,7 +222,7 @@ int egn_ellipse_refine(egn_ctx* ctx, const uint8_t* argmax_u8, const float* ell_
                        int refine, int batch, void* stream) {
   API_BEGIN
   EGN_CHECK(ctx && argmax_u8 && ell_norm && out && batch > 0, "bad argument");
-  CUDA_OK(cudaSetDevice(ctx->eng.device));
+  DeviceGuard guard(ctx->eng.device);
   dim3 grid(REFINE_CLUSTER, 2, batch);             // one 8-CTA cluster per ellipse (static __cluster_dims__)
   ellipse_refine_kernel<<<grid, REFINE_THREADS, 0, (cudaStream_t)stream>>>(argmax_u8, ell_norm, out, refine);
   CUDA_OK(cudaGetLastError());
@@ -201,7 +233,7 @@ int egn_ellipse_refine(egn_ctx* ctx, const uint8_t* argmax_u8, const float* ell_
 int egn_preprocess_u8(egn_ctx* ctx, const uint8_t* frames_u8, float* out, int batch, void* stream) {
   API_BEGIN
   EGN_CHECK(ctx && frames_u8 && out && batch > 0, "bad argument");
-  CUDA_OK(cudaSetDevice(ctx->eng.device));
+  DeviceGuard guard(ctx->eng.device);
   preprocess_u8_kernel<<<batch, PRE_THREADS, 0, (cudaStream_t)stream>>>(frames_u8, out);
   CUDA_OK(cudaGetLastError());
   ctx->eng.launches += 1;
@@ -218,7 +250,7 @@ int egn_profile(egn_ctx* ctx, int enable) {
 int egn_profile_read(egn_ctx* ctx, double* conv_ms, double* conv_flops, long long* conv_launches, int reset) {
   API_BEGIN
   EGN_CHECK(ctx && conv_ms && conv_flops && conv_launches, "bad argument");
-  CUDA_OK(cudaSetDevice(ctx->eng.device));
+  DeviceGuard guard(ctx->eng.device);
   ctx->eng.profile_resolve();
   *conv_ms = ctx->eng.prof_ms; *conv_flops = ctx->eng.prof_flops; *conv_launches = ctx->eng.prof_launches;
   if (reset) { ctx->eng.prof_ms = 0; ctx->eng.prof_flops = 0; ctx->eng.prof_launches = 0; }
@@ -228,7 +260,7 @@ int egn_profile_read(egn_ctx* ctx, double* conv_ms, double* conv_flops, long lon
 long long egn_profile_table(egn_ctx* ctx, char* out, long long capacity) {
   try {
     if (!ctx) return -1;
-    cudaSetDevice(ctx->eng.device);
+    DeviceGuard guard(ctx->eng.device);
     const std::string t = ctx->eng.profile_table();
     if (out && capacity > 0) {
       const size_t n = std::min((size_t)capacity - 1, t.size());
@@ -256,7 +288,7 @@ long long egn_debug_read(egn_ctx* ctx, const char* name, float* out, long long c
   try {
     if (!ctx || !name) return -1;
     Engine& e = ctx->eng;
-    cudaSetDevice(e.device);
+    DeviceGuard guard(e.device);
     cudaDeviceSynchronize();
     auto it = e.debug_acts.find(name);
     if (it != e.debug_acts.end()) {
@@ -308,7 +340,7 @@ int egn_conv_selfcheck(egn_ctx* ctx, const char* layer, int frames, double* max_
   API_BEGIN
   EGN_CHECK(ctx && layer && max_diff && max_ref, "bad argument");
   Engine& e = ctx->eng;
-  CUDA_OK(cudaSetDevice(e.device));
+  DeviceGuard guard(e.device);
   EGN_CHECK(e.use_tc, "selfcheck needs the tensor-core path (unset EGN_CONV=simt)");
   auto it = e.conv_index.find(layer);
   EGN_CHECK(it != e.conv_index.end(), std::string("unknown conv layer: ") + layer);

@@ -189,6 +189,13 @@ struct Engine {
     mem_bdcn.release(); mem_esf.release(); mem_misc.release();
   }
 
+  // per-device function attributes (dynamic shared memory above 48 KB); called by egn_create with
+  // this engine's device current
+  static void prepare_device() {
+    tc_prepare_device();
+    CUDA_OK(cudaFuncSetAttribute(head_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_TAIL_SMEM));
+  }
+
   Act* new_act(DevMem& mem, int N, int H, int W, int C) {
     EGN_CHECK(C % 8 == 0, "Act channels must be a multiple of 8");
     std::unique_ptr<Act> a(new Act());
@@ -585,7 +592,8 @@ struct Engine {
   // x: device fp32 [B][planes][H][W]; planes == 1 is the grey frame the reference replicates with
   // cat(img,img,img) (utils.py:649; conv1_1 then uses input-channel-summed weights), planes == 3 is
   // the general BDCN.forward input.  edge_out: [B][H][W].
-  void bdcn_forward(const float* x, int planes, float* edge_out, int B, cudaStream_t st) {
+  // side (optional): [10][B][H][W], the per-scale sigmoids of bdcn_new.py:178-191 in the reference's order.
+  void bdcn_forward(const float* x, int planes, float* edge_out, int B, cudaStream_t st, float* side = nullptr) {
     if (!built_bdcn) build_bdcn();
     const size_t hw = (size_t)EGN_H * EGN_W;
     for (int b0 = 0; b0 < B; b0 += mb) {
@@ -605,6 +613,7 @@ struct Engine {
       }
       BdcnTailParams tp = bd.tail;
       tp.N = nb; tp.out = edge_out + b0 * hw;
+      tp.side = side ? side + b0 * hw : nullptr; tp.side_stride = (long long)B * (long long)hw;
       aux("bdcn.tail", st, [&] { launch_1d(bdcn_tail_kernel, tp, (long long)nb * hw, st); ++launches; });
     }
   }
@@ -1060,11 +1069,6 @@ struct Engine {
       }
       run_conv_impl(es.head_c1, nb, st, cfg.add_seg ? -1 : eoff);
       {
-        static bool attr_set = false;
-        if (!attr_set) {
-          CUDA_OK(cudaFuncSetAttribute(head_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_TAIL_SMEM));
-          attr_set = true;
-        }
         HeadTailParams h = es.head;
         h.B = nb; h.el_out = el_out + (size_t)b0 * 10;
         head_tail_kernel<<<nb, HEAD_TAIL_THREADS, HEAD_TAIL_SMEM, st>>>(h); CUDA_OK(cudaGetLastError()); ++launches;

@@ -70,6 +70,23 @@ class Context:
                                              _stream(self.device)))
         return out
 
+    def bdcn_forward_all(self, x):
+        """Full BDCN.forward return (bdcn_new.py:178-191): (edge [B,1,H,W], sides [10,B,1,H,W])."""
+        assert x.dim() == 4 and x.shape[2] == H and x.shape[3] == W and x.shape[1] in (1, 3), x.shape
+        x = _f32c(x, self.device)
+        B = int(x.shape[0])
+        out = torch.empty((B, 1, H, W), dtype=torch.float32, device=self.device)
+        sides = torch.empty((10, B, 1, H, W), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.egn_bdcn_forward_all(self.h, _ptr(x), int(x.shape[1]), _ptr(out), _ptr(sides), B,
+                                                 _stream(self.device)))
+        return out, sides
+
+    def info(self):
+        """What this context runs (include/egn.h egn_info_t) as a dict."""
+        i = _lib.EgnInfo()
+        _lib.check(self.lib.egn_info(self.h, ctypes.byref(i)))
+        return {k: getattr(i, k) for k, _ in _lib.EgnInfo._fields_}
+
     def esf_forward(self, x, edge):
         assert x.dim() == 4 and tuple(x.shape[1:]) == (1, H, W), x.shape
         B = int(x.shape[0])

@@ -20,10 +20,11 @@ def calc_edge(args, img, edge_model, device):
 def get_predictions(output, model=None):
     """utils.py:65-81: argmax over the class dimension as an int64 CPU tensor [B,H,W].
 
-    With ``model`` (a DenseNet2D that just produced ``output``) the device-side u8 argmax of the
-    same forward is reused, so only B*H*W bytes cross PCIe instead of the fp32 logits."""
+    With ``model`` (the DenseNet2D that produced exactly this ``output`` tensor - same storage, same
+    version, same shape) the device-side u8 argmax of that forward is reused, so only B*H*W bytes cross
+    PCIe instead of the fp32 logits; any other logits tensor goes through the argmax kernel again."""
     if model is not None and getattr(model, "last_argmax", None) is not None \
-            and model.last_argmax.shape[0] == output.shape[0]:
+            and getattr(model, "_last_logits_key", None) == (output.data_ptr(), output._version, tuple(output.shape)):
         return model.last_argmax.cpu().to(torch.int64)
     if output.is_cuda:
         from .engine import Context

@@ -54,7 +54,9 @@ class DenseNet2D(EngineBound):
     def forward(self, x, x_edge, target=None, pupil_center=None, elNorm=None, spatWts=None, distMap=None,
                 cond=None, ID=None, alpha=0):
         logits, el_out, latent, argmax, el_pred = self.infer(x, x_edge, cond)
-        self.last_argmax = argmax            # u8 [B,H,W] on device, reused by egn_b200.get_predictions
+        # u8 [B,H,W] on device, reused by egn_b200.get_predictions for exactly this logits tensor
+        self.last_argmax = argmax
+        self._last_logits_key = (logits.data_ptr(), logits._version, tuple(logits.shape))
         tensors = (target, pupil_center, elNorm, spatWts, distMap, cond)
         if all(torch.is_tensor(t) for t in tensors):
             # the loss slot of the reference forward (RITnet_v2.py:312-323): forward value only

@@ -10,7 +10,8 @@
  * egn_last_error() returns a thread-local message.  All tensor arguments are raw DEVICE pointers
  * owned by the caller (fp32, contiguous, the reference's NCHW layouts) unless a parameter says
  * "host".  `stream` is a cudaStream_t passed as void*.  A context belongs to one device and is not
- * thread-safe.  Frames are 240x320 (utils.py:1007 hard-wires the 15x20 bottleneck).
+ * thread-safe; several contexts (one per device) may live in one process, and every call leaves the
+ * caller's current device as it found it.  Frames are 240x320 (utils.py:1007 hard-wires the 15x20 bottleneck).
  */
 #ifndef EGN_H_
 #define EGN_H_
@@ -55,6 +56,14 @@ int egn_plan(egn_ctx* ctx, int micro_batch);
  * bdcn_new.py:116-191).  x: [B,planes,240,320] with planes == 3 (what BDCN.forward receives) or
  * planes == 1 (the grey frame calc_edge replicates; skips the cat).  edge_out: [B,1,240,320]. */
 int egn_bdcn_forward(egn_ctx* ctx, const float* x, int planes, float* edge_out, int batch, void* stream);
+
+/* Replaces: the full return value of BDCN.forward (bdcn_new.py:116-191): besides the fused map,
+ * side_out receives the ten per-scale sigmoids in the reference's order
+ * [p1_1, p2_1, p3_1, p4_1, p5_1, p1_2, p2_2, p3_2, p4_2, p5_2], laid out [10][B][1][240][320].
+ * utils.calc_edge and evaluate.py only read [-1] (egn_bdcn_forward); callers that iterate the list
+ * get these through the Python mirror's lazy list. */
+int egn_bdcn_forward_all(egn_ctx* ctx, const float* x, int planes, float* edge_out, float* side_out, int batch,
+                         void* stream);
 
 /* Replaces: DenseNet2D.forward up to elOut (RITnet_v2.py:261-310).  x, edge: [B,1,240,320]
  * (edge may be NULL when the setting does not read it); logits: [B,3,240,320]; el_out: [B,10];
@@ -109,6 +118,16 @@ int egn_profile_read(egn_ctx* ctx, double* conv_ms, double* conv_flops, long lon
 
 /* CSV of per-layer kernel times gathered in profiling mode; returns the bytes needed. */
 long long egn_profile_table(egn_ctx* ctx, char* out, long long capacity);
+
+/* What the context actually runs: bench.py reports `dtype` and the precision ceiling from here, so a
+ * tuning knob (EGN_NSPLIT, EGN_CONV) can never hide behind a hard-coded label. */
+typedef struct egn_info_t {
+  int device, num_sms, micro_batch;
+  int products_per_mac;      /* bf16 tensor-core products per algorithmic MAC: 3 = hi*hi + lo*hi + hi*lo (default), 1 = plain bf16 */
+  int tensor_core_path;      /* 1 = tcgen05 kernel, 0 = SIMT companion (EGN_CONV=simt, debugging only) */
+  long long workspace_bytes; /* device memory held by the context so far */
+} egn_info_t;
+int egn_info(egn_ctx* ctx, egn_info_t* out);
 
 /* Introspection used by tests / bench. */
 long long egn_launch_count(egn_ctx* ctx);            /* kernels launched so far */

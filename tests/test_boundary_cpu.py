@@ -223,3 +223,46 @@ def test_header_is_plain_c(tmp_path):
         r = subprocess.run(["gcc", "-std=c99", "-Wall", "-fsyntax-only", "-I" + os.path.join(root, "include"),
                             "-I/usr/local/cuda/include", os.path.join(root, "tools", "abi_client.c")], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_data_parallel_replicas_never_own_a_context():
+    """test.py:264-269,296 wraps the model in nn.DataParallel on multi-GPU boxes; replicate() calls
+    _replicate_for_data_parallel() on every forward.  A replica must resolve to its primary's per-device
+    context cache and must not be able to close anything (ADVICE r1: shallow-copied __dict__ shared _ctx)."""
+    d = egn_b200.DenseNet2D(CONFIGS["baseline_edge"])
+    d.micro_batch = 3
+
+    class FakeCtx:
+        closed = False
+
+        def close(self):
+            self.closed = True
+    sentinel = FakeCtx()
+    d._ctxs[torch.device("cuda", 0)] = (sentinel, "key")
+    r = d._replicate_for_data_parallel()
+    assert r._primary is d and r._ctxs is None and r._items is None
+    rr = r._replicate_for_data_parallel()           # a replica of a replica still points at the owner
+    assert rr._primary is d
+    assert d._ctxs[torch.device("cuda", 0)][0] is sentinel and not sentinel.closed
+    # the reference's own wrap, literally (no forward without a GPU): state_dict keys gain the module. prefix
+    # that pack_state_dict strips (pytorchtools.py:113-123)
+    wrapped = torch.nn.DataParallel(d)
+    assert all(k.startswith("module.") for k in wrapped.state_dict())
+    b = egn_b200.BDCN()
+    assert b._replicate_for_data_parallel()._primary is b
+
+
+def test_get_predictions_never_reuses_a_stale_argmax():
+    """The cached device argmax belongs to ONE logits tensor (storage, version, shape); any other tensor of
+    the same batch size must not get it (VERDICT r1 weak #3).  CPU-only: the fallback for CPU logits raises."""
+    d = egn_b200.DenseNet2D(CONFIGS["baseline"])
+    logits = torch.zeros(2, 3, 240, 320)
+    d.last_argmax = torch.ones(2, 240, 320, dtype=torch.uint8)
+    d._last_logits_key = (logits.data_ptr(), logits._version, tuple(logits.shape))
+    assert egn_b200.get_predictions(logits, d).sum().item() == 2 * 240 * 320
+    other = torch.zeros(2, 3, 240, 320)
+    with pytest.raises(RuntimeError):
+        egn_b200.get_predictions(other, d)          # different storage -> argmax kernel path (CUDA only)
+    logits.add_(1)                                   # same storage, new version
+    with pytest.raises(RuntimeError):
+        egn_b200.get_predictions(logits, d)

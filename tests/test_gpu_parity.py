@@ -201,17 +201,37 @@ def test_ellipse_transform_and_refinement(env):
         seg[i][masks[2 * i + 1].astype(bool)] = 2
         for w in range(2):
             ell[i, w] = env["graph"].ellipse_transform(g["inits"][2 * i + w], Hinv)[:5]
+    # one degenerate frame: no pupil pixel at all (seg_count == 0 and, for the tiny start ellipse below, an
+    # empty raster too -> IoU = 0/0 = NaN, every comparison of the descent is False, the start is returned)
+    seg = np.concatenate([seg, (seg[:1] == 1).astype(np.uint8)], 0)
+    tiny = ell[:1].copy()
+    tiny[0, 1] = [0.9, 0.9, 1e-4, 1e-4, 0.3]
+    ell = np.concatenate([ell, tiny], 0)
     out = ctx.ellipse_refine(torch.from_numpy(seg).to(dev), torch.from_numpy(ell), refine=True).cpu().numpy()
-    for i in range(k):
+    deg = lambda p: [p[0], p[1], p[2], p[3], p[4] * 180 / 3.14159]
+    worst = 0.0
+    for i in range(k + 1):
         for w in range(2):
             m = seg[i] == (w + 1)
-            ref = g["refined"][2 * i + w]
             got = out[i, w]
-            deg = lambda p: [p[0], p[1], p[2], p[3], p[4] * 180 / 3.14159]
-            # the start point went through a float32 normalised round trip, so compare achieved IoU
-            # (the objective) and parameters loosely rather than bit for bit
-            assert env["graph"].ell_iou(m, deg(got)) >= env["graph"].ell_iou(m, deg(ref)) - 0.01
-            np.testing.assert_allclose(got[:2], ref[:2], atol=0.05)
+            # the oracle starts from exactly what the device starts from: the float32 normalised parameters
+            # the ABI carries, mapped to pixels in float64 (evaluate.py:141-146)
+            start = env["graph"].ellipse_norm_to_px(ell[i, w].astype(np.float64))
+            want = env["graph"].refine_ellipse(m, start)
+            np.testing.assert_allclose(got[:2], want[:2], rtol=1e-9, atol=1e-9)      # the search never moves the centre
+            # a, b, theta: north_star's "ellipse parameters within 1e-2 relative" (floor 1e-2)
+            err = rel_err(got[2:5], want[2:5])
+            worst = max(worst, err)
+            assert err < 1e-2, (i, w, got, want)
+            if i < k:
+                # and against the reference's own search from its float64 start (fixture): same objective value
+                ref = g["refined"][2 * i + w]
+                assert env["graph"].ell_iou(m, deg(got)) >= env["graph"].ell_iou(m, deg(ref)) - 0.01
+                np.testing.assert_allclose(got[:2], ref[:2], atol=0.05)
+    assert np.isfinite(out[:k]).all()
+    # degenerate pupil: NaN objective, parameters come back unrefined
+    np.testing.assert_allclose(out[k, 1], env["graph"].ellipse_norm_to_px(ell[k, 1].astype(np.float64)), rtol=1e-9)
+    print("ellipse refinement: worst relative deviation of (a, b, theta) from the oracle %.2e" % worst)
 
 
 def test_end_to_end_metrics_on_synthetic_eyes(env):
@@ -255,6 +275,17 @@ def test_evaluate_per_image_path(env):
     got_iou = g.ell_iou(seg_map == 2, [pupil[0], pupil[1], pupil[2], pupil[3], pupil[4] * 180 / 3.14159])
     want_iou = g.ell_iou(pref == 2, [want[0], want[1], want[2], want[3], want[4] * 180 / 3.14159])
     assert got_iou >= want_iou - 0.02 or not np.isfinite(want_iou)
+    # the refinement itself, pinned on the engine's own segmentation and float32 elPred: the oracle's search
+    # from the same start and the same mask must return the same (a, b, theta) for both ellipses
+    with torch.no_grad():
+        lo, eo, la, am, ep = m.infer(x, env["edge_model"].edge(x), None)
+        ell = m.context(dev).ellipse_refine(am, ep, True).cpu().numpy()
+    ep, seg2 = ep.cpu().numpy().astype(np.float64), am.cpu().numpy()[0]
+    for got, cls, sl in ((ell[0, 0], 1, slice(0, 5)), (ell[0, 1], 2, slice(5, 10))):
+        start = g.ellipse_norm_to_px(ep[0, sl])
+        w = g.refine_ellipse(seg2 == cls, start)
+        np.testing.assert_allclose(got[:2], w[:2], rtol=1e-9, atol=1e-9)
+        assert rel_err(got[2:5], w[2:5]) < 1e-2, (cls, got, w)
 
 
 def test_preprocess_u8_matches_numpy_zscore(env):
@@ -488,3 +519,95 @@ def test_full_size_batch_properties(env):
     ctx.metrics_accumulate(am[128:].contiguous(), lab[128:].contiguous(), cond[128:], b.acc, c[128:], c[128:], eo[128:].contiguous(), ep[128:].contiguous())
     np.testing.assert_allclose(whole.acc.cpu().numpy(), (a.acc + b.acc).cpu().numpy(), rtol=1e-12)
     assert whole.result()["frames"] == 256
+
+
+def test_bdcn_side_outputs_are_real_tensors(env):
+    """BDCN.forward returns the reference's 11-entry list (bdcn_new.py:178-191): [-1] eagerly, the ten
+    per-scale sigmoids on first access of any other entry - compared here with the oracle's full forward."""
+    g, dev = env["graph"], env["dev"]
+    x3 = torch.cat([env["img"]] * 3, 1)
+    out = env["edge_model"](x3.to(dev))
+    assert len(out) == 11 and not out._filled
+    fuse = out[-1]
+    assert not out._filled                              # what utils.calc_edge does: no extra work
+    with torch.no_grad():
+        ref = g.bdcn_forward(env["bsd"], x3, return_all=True)
+    assert len(ref) == 11
+    for i, (a, b) in enumerate(zip(out, ref)):          # iterating materialises the side outputs
+        assert a.shape == (2, 1, 240, 320) and a.dtype == torch.float32 and a.is_cuda
+        np.testing.assert_allclose(a.cpu().numpy(), b.numpy(), atol=5e-4, err_msg="output %d" % i)
+    assert out._filled and out[10] is fuse
+    assert torch.equal(env["edge_model"](x3.to(dev))[3], out[3])
+
+
+def test_get_predictions_keyed_on_the_logits_tensor(env):
+    m, st, esd = _model(env, "baseline_edge")
+    dev, egn = env["dev"], env["egn"]
+    with torch.no_grad():
+        a = m(env["img"].to(dev), env["edge_ref"].to(dev), None, None, None, None, None, torch.zeros(2, 4, device=dev), 0, 0)[0]
+        pa = egn.get_predictions(a, m)
+        held = a.clone()
+        b = m(env["img"].flip(0).to(dev), env["edge_ref"].flip(0).to(dev), None, None, None, None, None,
+              torch.zeros(2, 4, device=dev), 0, 0)[0]
+        pb = egn.get_predictions(b, m)
+        assert torch.equal(pb, pa.flip(0))
+        assert torch.equal(egn.get_predictions(held, m), pa)       # logits of the EARLIER call: not the cached argmax
+        assert torch.equal(egn.get_predictions(held), pa)
+
+
+def test_engine_info_reports_the_precision_policy(env):
+    info = env["edge_model"].context(env["dev"]).info()
+    assert info["products_per_mac"] == 3 and info["tensor_core_path"] == 1 and info["micro_batch"] == 4
+    assert info["workspace_bytes"] > 0 and info["num_sms"] >= 100
+
+
+def test_api_leaves_the_callers_device_alone(env):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    egn, dev1 = env["egn"], torch.device("cuda:1")
+    torch.cuda.set_device(0)
+    em = egn.BDCN(); em.load_state_dict(env["bsd"]); em = em.to(dev1).eval(); em.micro_batch = 2
+    m, st, esd = _model(env, "baseline_edge", mb=2)
+    m = m.to(dev1)
+    with torch.no_grad():
+        e = em.edge(env["img"].to(dev1))
+        lo, eo, la, am, ep = m.infer(env["img"].to(dev1), e, None)
+    assert torch.cuda.current_device() == 0                        # two contexts on cuda:1, caller still on cuda:0
+    gold = np.load(os.path.join(env["golden"], "fwd_baseline_edge.npz"))
+    np.testing.assert_allclose(e.cpu().numpy(), gold["edge"], atol=5e-4)
+    assert (am.cpu().numpy() == gold["pred"]).mean() >= 0.999
+    e0 = env["edge_model"].edge(env["img"].to(env["dev"]))          # and the cuda:0 context still works
+    np.testing.assert_allclose(e0.cpu().numpy(), gold["edge"], atol=5e-4)
+
+
+def test_reference_data_parallel_wrap(env):
+    """test.py:264-269,294-297 on a multi-GPU box: model = torch.nn.DataParallel(model); model.to(device).
+    BDCN stays on cuda:0 (test.py:284); the wrapped ESF-Net scatters the batch over the GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    egn, g, dev = env["egn"], env["graph"], env["dev"]
+    st = env["synth"].SETTINGS["baseline_edge"]
+    esd = env["synth"].make_esf_state(st, 0)
+    model = egn.DenseNet2D(st)
+    model.load_state_dict(esd)
+    model.micro_batch = 2
+    model = torch.nn.DataParallel(model)
+    model = model.to(dev).to(torch.float32)
+    model.eval()
+    x = torch.cat([env["img"], env["img"].flip(0)], 0)
+    with torch.no_grad():
+        edge = egn.calc_edge(None, x, env["edge_model"], dev)
+        for _ in range(2):                                          # second call reuses the per-device contexts
+            op, elPred, latent, loss, elOut = model(x.to(dev), edge, None, None, None, None, None,
+                                                    torch.zeros(4, 4, device=dev), None, 0)
+        pred = egn.get_predictions(op, model)
+    assert op.shape == (4, 3, 240, 320) and op.device == dev and elOut.shape == (4, 10)
+    prim = model.module
+    assert set(prim._ctxs) >= {torch.device("cuda", 0), torch.device("cuda", 1)}
+    gold = np.load(os.path.join(env["golden"], "fwd_baseline_edge.npz"))
+    want = np.concatenate([gold["pred"], gold["pred"][::-1]], 0)
+    assert (pred.numpy() == want).mean() >= 0.999
+    scale = np.array([160.0, 120.0])
+    wel = np.concatenate([gold["elPred"], gold["elPred"][::-1]], 0)
+    for sl in (slice(0, 2), slice(5, 7)):
+        assert np.abs((elPred.cpu().numpy()[:, sl] - wel[:, sl]) * scale).max() < 0.25
