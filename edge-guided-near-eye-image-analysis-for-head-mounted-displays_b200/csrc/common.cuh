@@ -129,6 +129,7 @@ struct ConvEpi {
   // CONV_MSBLOCK: v = o + sum_g relu(acc_g + b_g); score[p][j] (+)= v . score_w[j]
   const bf16* o_hi;
   const bf16* o_lo;
+  int o_C, o_coff;         // channels of the buffer holding o and its first channel there
   const float* score_w;    // [2][32]
   float* score;            // [N][H][W][2]
   int score_accum;

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(ST_THREADS) conv_simt_kernel(const SimtParams 
     float s0 = 0.f, s1 = 0.f;
     if (valid) {
       float o[8];
-      load8(p.e.o_hi, p.e.o_lo, pix * 32 + cog * 8, o);
+      load8(p.e.o_hi, p.e.o_lo, pix * p.e.o_C + p.e.o_coff + cog * 8, o);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int ch = cog * 8 + i;

@@ -46,6 +46,10 @@ struct TcParams {
   int acc_bufs;                        // TMEM accumulator buffers (1 or 2)
   int n_aloads;
   int l2_prefetch;                     // producer prefetches its next tile's activation boxes into L2
+  // upsample-add layers: the half-resolution operand patch of a tile ((tr/2 + 2) x (bw/2 + 2) pixels x n_tile
+  // channels, both planes) is staged in shared memory by the epilogue warps with cp.async, one tile ahead
+  int up_rows, up_cols;                // patch rows / columns (half-resolution pixels)
+  uint32_t up_pix_stride, up_plane_stride, up_patch_bytes;
   int dbg;                             // timing experiments only: 1 = skip epilogue body, 2 = skip MMAs, 4 = skip activation TMA loads, 8 = skip weight TMA loads
   int8_t aload_dx[TC_MAX_ALOADS];
   uint8_t aload_tap0[TC_MAX_ALOADS], aload_ntaps[TC_MAX_ALOADS];
@@ -193,6 +197,29 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
 
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+// 8 channels of one staged half-resolution pixel: hi plane at `a`, lo plane `plane` bytes further
+__device__ __forceinline__ void lds_px8(uint32_t a, uint32_t plane, float t[8]) {
+  const uint4 h = lds128(a), l = lds128(a + plane);
+  const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    t[2 * i] = __uint_as_float(hh[i] << 16) + __uint_as_float(ll[i] << 16);
+    t[2 * i + 1] = __uint_as_float(hh[i] & 0xffff0000u) + __uint_as_float(ll[i] & 0xffff0000u);
+  }
 }
 
 __device__ __forceinline__ bool elect_one() {
@@ -345,6 +372,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   TcTapStep* s_tap = reinterpret_cast<TcTapStep*>(c_shift + 512);
   TcChunk* s_chunk = reinterpret_cast<TcChunk*>(s_tap + 32);
   TcLoad* s_load = reinterpret_cast<TcLoad*>(s_chunk + EGN_MAX_CHUNKS);
+  const uint32_t up_base = smem_u32(s_load + TC_MAX_ALOADS);   // two staged half-resolution patches (UP layers only)
   if ((int)threadIdx.x < p.g.ntaps) {
     const int t = threadIdx.x;
     TcTapStep st;
@@ -671,6 +699,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int mr = m >> p.bw_log2, mc = m & (bw - 1);
     int stat_flip = 0;
     int use = 0;
+    // upsample-add layers (decoder 1x1 convolutions): copies the (tr/2 + 2) x (bw/2 + 2) half-resolution pixels a
+    // tile blends (indices clamped like F.interpolate, align_corners=False) x n_tile channels x both planes
+    // into shared memory with cp.async, 16 bytes per request; issued one tile ahead so that the L2 / HBM
+    // latency hides behind the previous tile's epilogue instead of stalling this one
+    auto up_stage = [&](int t, int buf) {
+      const int nb2 = t % p.n_blocks;
+      int rest2 = t / p.n_blocks;
+      const int tx2 = rest2 % p.tiles_x;
+      rest2 /= p.tiles_x;
+      const int ty2 = rest2 % p.tiles_y;
+      const int n2 = rest2 / p.tiles_y;
+      const int Hi = p.g.H >> 1, Wi = p.g.W >> 1;
+      const int y0 = ((ty2 * p.tr) >> 1) - 1, x0 = ((tx2 * bw) >> 1) - 1;
+      const int c8n = p.n_tile >> 3;
+      const int per_plane = p.up_rows * p.up_cols * c8n;
+      const uint32_t dst0 = up_base + (uint32_t)buf * p.up_patch_bytes;
+      const size_t cbase = (size_t)p.e.up_coff + (size_t)nb2 * p.n_tile;
+      for (int i = (int)threadIdx.x - 64; i < 2 * per_plane; i += TC_EPI_WARPS * 32) {
+        const int plane = i >= per_plane ? 1 : 0;
+        int r = i - plane * per_plane;
+        const int c8 = r % c8n;
+        r /= c8n;
+        const int col = r % p.up_cols, row = r / p.up_cols;
+        const int yy = min(max(y0 + row, 0), Hi - 1), xx = min(max(x0 + col, 0), Wi - 1);
+        const bf16* src = (plane ? p.e.up_lo : p.e.up_hi) + (((size_t)n2 * Hi + yy) * Wi + xx) * p.e.up_C + cbase + c8 * 8;
+        cp_async16(dst0 + plane * p.up_plane_stride + (uint32_t)(row * p.up_cols + col) * p.up_pix_stride + c8 * 16, src);
+      }
+      cp_async_commit();
+    };
+    if (UP && (int)blockIdx.x < p.total_tiles) up_stage(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++use) {
       const int nb = tile % p.n_blocks;
       int rest = tile / p.n_blocks;
@@ -683,29 +741,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t aphase = (p.acc_bufs == 2 ? (use >> 1) : use) & 1u;
       const int px = tx * bw + mc;
 
-      // upsample-add layers: the half-resolution operands of this warp's first two sub-tiles are
-      // requested before the accumulator is awaited, and those of every later pair right after the
-      // previous pair has been consumed, so their L2 latency hides behind TMEM loads and stores
-      float L[2][UP ? 16 : 1];
-      auto up_fetch = [&](int g, int s0) {
-        const int rw = 32 >> p.bw_log2, lcols = (bw >> 1) + 2, lrows = (rw >> 1) + 2;
-        const int Hi = p.g.H >> 1, Wi = p.g.W >> 1;
-        const int lr = min(lane / lcols, lrows - 1), lc = lane % lcols;
-        const int xx = min(max(((tx * bw) >> 1) - 1 + lc, 0), Wi - 1);
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          if (UP && s0 + u < nsub) {
-            const int py0 = ty * p.tr + (s0 + u) * p.sr + quarter * rw;             // first output row of this warp
-            const int yy = min(max((py0 >> 1) - 1 + lr, 0), Hi - 1);
-            load16(p.e.up_hi, p.e.up_lo, (((size_t)n * Hi + yy) * Wi + xx) * p.e.up_C + p.e.up_coff + nb * p.n_tile + (g << 4), L[u]);
-          }
-        }
-      };
-      if (UP && half < (p.n_tile >> 4)) up_fetch(half, 0);
-
       mbar_wait(tfull_bar(ab), aphase, p.err_flag, 6);
       fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * TC_ACC_STRIDE;
+      if (UP) {
+        // this tile's half-resolution patch has landed (everybody's copies), and everybody is done reading the
+        // other buffer (they are past the previous tile): refill it with the next tile's patch
+        cp_async_wait_all();
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (tile + (int)gridDim.x < p.total_tiles) up_stage(tile + gridDim.x, (use + 1) & 1);
+      }
+      const uint32_t up_buf = up_base + (uint32_t)(use & 1) * p.up_patch_bytes;
 
       if (p.dbg & 1) {
       } else if (p.e.mode == CONV_STORE || p.e.mode == CONV_LOGITS) {
@@ -748,23 +794,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const size_t pix = ((size_t)n * p.g.H + py) * p.g.W + px;
                 float v[16];
                 if (UP) {
-                  // + bilinear x2 upsample of the half-resolution tensor (common.cuh upsample_add): the 32
-                  // output pixels of this warp (rw rows x bw columns, rw * bw = 32) blend (rw/2 + 2) x (bw/2 + 2)
-                  // <= 30 half-resolution pixels; each lane loaded ONE of them (up_fetch: 16 channels, 2 x 32 bytes,
-                  // indices clamped like F.interpolate) and the blends are assembled with shuffles.
-                  const int lcols = (bw >> 1) + 2;
-                  const int wr = lane >> p.bw_log2;                                   // my row / column inside the warp's patch
-                  const int la = (wr >> 1) + (wr & 1), lca = (mc >> 1) + (mc & 1);    // even: (l-1, l), odd: (l, l+1) with l = (r>>1)+1
-                  const float wya = (wr & 1) ? 0.75f : 0.25f, wyb = 1.f - wya;
-                  const float wxa = (mc & 1) ? 0.75f : 0.25f, wxb = 1.f - wxa;
-                  const int s00 = la * lcols + lca, s10 = s00 + lcols;
+                  // + bilinear x2 upsample of the half-resolution tensor (same arithmetic as common.cuh upsample_add)
+                  // from the staged patch: for o = 2i the taps are (i-1, i) with weights (0.25, 0.75), for o = 2i+1
+                  // (i, i+1) with (0.75, 0.25), indices clamped to the frame
+                  const int Hi = p.g.H >> 1, Wi = p.g.W >> 1;
+                  const int iy = py >> 1, jx = px >> 1;
+                  const int y0 = ((ty * p.tr) >> 1) - 1, x0 = ((tx * bw) >> 1) - 1;
+                  const int ya = min((py & 1) ? iy : max(iy - 1, 0), Hi - 1), yb = min((py & 1) ? iy + 1 : iy, Hi - 1);
+                  const int xa = min((px & 1) ? jx : max(jx - 1, 0), Wi - 1), xb = min((px & 1) ? jx + 1 : jx, Wi - 1);
+                  const int ra = min(ya - y0, p.up_rows - 1), rb = min(yb - y0, p.up_rows - 1);
+                  const int ca = min(xa - x0, p.up_cols - 1), cc = min(xb - x0, p.up_cols - 1);
+                  const float wya = (py & 1) ? 0.75f : 0.25f, wyb = 1.f - wya;
+                  const float wxa = (px & 1) ? 0.75f : 0.25f, wxb = 1.f - wxa;
+                  const uint32_t chb = up_buf + (uint32_t)c0 * 2u;
+                  const uint32_t a00 = chb + (uint32_t)(ra * p.up_cols + ca) * p.up_pix_stride, a01 = chb + (uint32_t)(ra * p.up_cols + cc) * p.up_pix_stride;
+                  const uint32_t a10 = chb + (uint32_t)(rb * p.up_cols + ca) * p.up_pix_stride, a11 = chb + (uint32_t)(rb * p.up_cols + cc) * p.up_pix_stride;
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) {
-                    const float lv = L[u][UP ? i : 0];
-                    const float t00 = __shfl_sync(0xffffffffu, lv, s00), t01 = __shfl_sync(0xffffffffu, lv, s00 + 1);
-                    const float t10 = __shfl_sync(0xffffffffu, lv, s10), t11 = __shfl_sync(0xffffffffu, lv, s10 + 1);
-                    const float top = wxa * t00 + wxb * t01, bot = wxa * t10 + wxb * t11;
-                    v[i] = apply_act((__uint_as_float(r[u][i]) + bias[i]) + (wya * top + wyb * bot), p.e.act);
+                  for (int h8 = 0; h8 < 2; ++h8) {
+                    float t00[8], t01[8], t10[8], t11[8];
+                    lds_px8(a00 + h8 * 16, p.up_plane_stride, t00);
+                    lds_px8(a01 + h8 * 16, p.up_plane_stride, t01);
+                    lds_px8(a10 + h8 * 16, p.up_plane_stride, t10);
+                    lds_px8(a11 + h8 * 16, p.up_plane_stride, t11);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                      const int i = h8 * 8 + k;
+                      const float top = wxa * t00[k] + wxb * t01[k], bot = wxa * t10[k] + wxb * t11[k];
+                      v[i] = apply_act((__uint_as_float(r[u][i]) + bias[i]) + (wya * top + wyb * bot), p.e.act);
+                    }
                   }
                 } else {
 #pragma unroll
@@ -792,10 +849,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                   }
                 }
               }
-            }
-            if (UP) {                              // request the next pair's half-resolution operands
-              if (s0 + 2 < nsub) up_fetch(g, s0 + 2);
-              else if (g + 2 < per_sub) up_fetch(g + 2, 0);
             }
           }
           if (p.e.stats) {
@@ -829,7 +882,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             float o[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = 0.f;
-            if (valid) load16(p.e.o_hi, p.e.o_lo, pix * 32 + c0, o);
+            if (valid) load16(p.e.o_hi, p.e.o_lo, pix * p.e.o_C + p.e.o_coff + c0, o);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -928,7 +981,8 @@ static void make_w_map(CUtensorMap* map, const bf16* ptr, int rows, int kpad, in
 static size_t tc_smem_bytes(const TcParams& p) {
   const int nplanes = p.nsplit == 1 ? 1 : 2;
   return 1024 + (size_t)p.na * nplanes * p.a_plane_bytes + (size_t)p.nw * p.w_slot_taps * nplanes * p.w_plane_bytes +
-         8 * (2 * p.na + 2 * p.nw + 4) + 16 + (2 * 2 * 4 * 32 + 768 + 512 + 512) * sizeof(float) + TC_SCHED_BYTES;
+         8 * (2 * p.na + 2 * p.nw + 4) + 16 + (2 * 2 * 4 * 32 + 768 + 512 + 512) * sizeof(float) + TC_SCHED_BYTES +
+         (p.e.up_hi ? 2 * (size_t)p.up_patch_bytes + 16 : 0);
 }
 
 // Fills the tiling fields of `p` from the geometry (taps must be sorted by dx) and sizes the rings.
@@ -1027,7 +1081,16 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   p.a_plane_bytes = (p.a_box_bytes + 1023u) & ~1023u;
   p.w_plane_bytes = (uint32_t)p.n_tile * 64u;
   const int nplanes = nsplit == 1 ? 1 : 2;
-  const size_t budget = 227 * 1024 - 1024 - 512 - 2048 - 7168 - TC_SCHED_BYTES;
+  // upsample-add layers stage two half-resolution patches next to the operand rings (pixel stride padded by
+  // 16 bytes so that the 16-byte reads of neighbouring pixels fall into different banks)
+  p.up_rows = p.up_cols = 0; p.up_pix_stride = p.up_plane_stride = p.up_patch_bytes = 0;
+  if (p.e.up_hi) {
+    p.up_rows = p.tr / 2 + 2; p.up_cols = (1 << p.bw_log2) / 2 + 2;
+    p.up_pix_stride = (uint32_t)p.n_tile * 2u + 16u;
+    p.up_plane_stride = (uint32_t)(p.up_rows * p.up_cols) * p.up_pix_stride;
+    p.up_patch_bytes = 2u * p.up_plane_stride;
+  }
+  const size_t budget = 227 * 1024 - 1024 - 512 - 2048 - 7168 - TC_SCHED_BYTES - (p.e.up_hi ? 2 * (size_t)p.up_patch_bytes + 16 : 0);
   const size_t a_slot = (size_t)nplanes * p.a_plane_bytes, w_slot = (size_t)nplanes * p.w_plane_bytes;
   // small N: an MMA is short (40-48 cycles) and the issue queue holds only ~8 of them, so the
   // per-tap barrier round trips of the weight ring would starve the pipe; load every tap of a box

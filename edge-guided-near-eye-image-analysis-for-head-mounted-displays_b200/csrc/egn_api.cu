@@ -343,7 +343,10 @@ int egn_conv_selfcheck(egn_ctx* ctx, const char* layer, int frames, double* max_
   DeviceGuard guard(e.device);
   EGN_CHECK(e.use_tc, "selfcheck needs the tensor-core path (unset EGN_CONV=simt)");
   auto it = e.conv_index.find(layer);
-  EGN_CHECK(it != e.conv_index.end(), std::string("unknown conv layer: ") + layer);
+  if (it == e.conv_index.end()) {
+    it = e.conv_alias.find(layer);
+    EGN_CHECK(it != e.conv_alias.end(), std::string("unknown conv layer: ") + layer);
+  }
   ConvLayer& L = *it->second;
   const int n = std::min(frames, L.g.batch);
   const size_t px = (size_t)n * L.g.H * L.g.W;

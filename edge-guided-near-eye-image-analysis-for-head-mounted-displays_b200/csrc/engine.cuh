@@ -137,6 +137,7 @@ struct Engine {
   std::map<std::string, std::pair<const float*, std::vector<int>>> debug_f32;
   std::vector<std::unique_ptr<Act>> acts;
   std::map<std::string, ConvLayer*> conv_index;
+  std::map<std::string, ConvLayer*> conv_alias;     // reference layer names of merged launches (lookup only)
 
   // ---- BDCN
   struct {
@@ -147,6 +148,8 @@ struct Engine {
     const float *first_w_gray, *first_w_rgb;
     ConvLayer vgg[13];           // index 0 unused (first_conv)
     ConvLayer ms_in[13], ms_tail[13];
+    bool merged[13];             // merged[i]: msblock i's `conv` rides as 32 extra output channels of vgg[i + 1] (same input map)
+    int f_c[13];                 // VGG channels of f[i] (a merged f[i] buffer holds 32 more: the MSBlock's `o`)
     BdcnTailParams tail;
   } bd;
 
@@ -459,9 +462,22 @@ struct Engine {
     static const int cout[13] = {64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512};
     static const int stage_of[13] = {0, 0, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4};
     const int sh[5] = {240, 120, 60, 30, 29}, sw_[5] = {320, 160, 80, 40, 39};
+    // msblock{s}_{j}.conv and features.conv{s}_{j+1} are both 3x3 / pad 1 / ReLU convolutions of the SAME map
+    // (bdcn_new.py:120-160, vgg16_c.py:65-88): where the dilations agree (stages 1-4) they run as ONE launch with
+    // the weight rows stacked, N = Cout_vgg + 32, writing [f | o] into one buffer whose channel windows the
+    // consumers read - the narrow N = 32 launch and one full read of the shared map disappear.
+    // EGN_MS_MERGE: bit s enables stage s + 1 (default: stages 1-3; 512 + 32 does not split into equal 16-aligned N tiles).
+    {
+      const int mask = getenv("EGN_MS_MERGE") ? atoi(getenv("EGN_MS_MERGE")) : 0x7;
+      for (int i = 0; i < 13; ++i) {
+        const bool next_same_stage = i + 1 < 13 && stage_of[i + 1] == stage_of[i];
+        bd.merged[i] = use_tc && next_same_stage && stage_of[i] < 3 && ((mask >> stage_of[i]) & 1);
+        bd.f_c[i] = cout[i];
+      }
+    }
     for (int i = 0; i < 13; ++i) {
       const int s = stage_of[i];
-      bd.f[i] = new_act(mem, mb, sh[s], sw_[s], cout[i]);
+      bd.f[i] = new_act(mem, mb, sh[s], sw_[s], cout[i] + ((i > 0 && bd.merged[i - 1]) ? 32 : 0));
       debug_acts[std::string("features.") + names[i]] = {bd.f[i], {0, cout[i]}};
     }
     const int pc[4] = {64, 128, 256, 512};
@@ -501,6 +517,24 @@ struct Engine {
       const int dil = s == 4 ? 2 : 1;
       const HostTensor& w = sd_get(sd, std::string("features.") + names[i] + ".weight");
       const HostTensor& b = sd_get(sd, std::string("features.") + names[i] + ".bias");
+      if (bd.merged[i - 1]) {
+        // rows [0, cout) = features.conv, rows [cout, cout + 32) = msblock.conv of the map both read
+        static const int blk_of[13] = {1, 2, 1, 2, 1, 2, 3, 1, 2, 3, 1, 2, 3};
+        const std::string mp = "msblock" + std::to_string(stage_of[i - 1] + 1) + "_" + std::to_string(blk_of[i - 1]);
+        const HostTensor& w0 = sd_get(sd, mp + ".conv.weight");
+        const HostTensor& b0 = sd_get(sd, mp + ".conv.bias");
+        EGN_CHECK(w0.shape[1] == cin[i] && w0.shape[0] == 32, mp + ".conv: unexpected weight shape");
+        std::vector<float> wc(w.data), bc(b.data);
+        wc.insert(wc.end(), w0.data.begin(), w0.data.end());
+        bc.insert(bc.end(), b0.data.begin(), b0.data.end());
+        build_conv(bd.vgg[i], mem, std::string("features.") + names[i] + "+" + mp + ".conv", {{in, 0, cin[i], 0}},
+                   {{wc.data(), bc.data(), dil, dil}}, cout[i] + 32, cin[i], 3, 3, sh[s], sw_[s], mb);
+        set_store_epilogue(bd.vgg[i], bd.f[i], 0, ACT_RELU);
+        finalize_conv(bd.vgg[i]);
+        conv_alias[std::string("features.") + names[i]] = &bd.vgg[i];
+        conv_alias[mp + ".conv"] = &bd.vgg[i];
+        continue;
+      }
       build_conv(bd.vgg[i], mem, std::string("features.") + names[i], {{in, 0, cin[i], 0}},
                  {{w.data.data(), b.data.data(), dil, dil}}, cout[i], cin[i], 3, 3, sh[s], sw_[s], mb);
       set_store_epilogue(bd.vgg[i], bd.f[i], 0, ACT_RELU);
@@ -524,10 +558,15 @@ struct Engine {
         const HostTensor& w0 = sd_get(sd, mp + ".conv.weight");
         const HostTensor& b0 = sd_get(sd, mp + ".conv.bias");
         ConvLayer& Lin = bd.ms_in[fi];
-        build_conv(Lin, mem, mp + ".conv", {{bd.f[fi], 0, cout[fi], 0}}, {{w0.data.data(), b0.data.data(), 1, 1}},
-                   32, cout[fi], 3, 3, sh[s], sw_[s], mb);
-        set_store_epilogue(Lin, bd.o[s], 0, ACT_RELU);
-        finalize_conv(Lin);
+        // `o` = relu(conv(f)): its own launch into the stage's o buffer, or (merged) channels [cout, cout + 32) of f[fi + 1]
+        const Act* o_buf = bd.merged[fi] ? bd.f[fi + 1] : bd.o[s];
+        const int o_off = bd.merged[fi] ? cout[fi + 1] : 0;
+        if (!bd.merged[fi]) {
+          build_conv(Lin, mem, mp + ".conv", {{bd.f[fi], 0, cout[fi], 0}}, {{w0.data.data(), b0.data.data(), 1, 1}},
+                     32, cout[fi], 3, 3, sh[s], sw_[s], mb);
+          set_store_epilogue(Lin, bd.o[s], 0, ACT_RELU);
+          finalize_conv(Lin);
+        }
         ConvLayer& Lt = bd.ms_tail[fi];
         std::vector<PackSpec> specs;
         for (int d = 1; d <= 3; ++d) {
@@ -535,7 +574,7 @@ struct Engine {
           const HostTensor& bdv = sd_get(sd, mp + ".conv" + std::to_string(d) + ".bias");
           specs.push_back({wd.data.data(), bdv.data.data(), 4 * d, 4 * d});
         }
-        build_conv(Lt, mem, mp + ".tail", {{bd.o[s], 0, 32, 0}}, specs, 32, 32, 3, 3, sh[s], sw_[s], mb);
+        build_conv(Lt, mem, mp + ".tail", {{o_buf, o_off, 32, 0}}, specs, 32, 32, 3, 3, sh[s], sw_[s], mb);
         // collapsed conv{s}_{j}_down -> score_dsn{s}, score_dsn{s}_1 (both linear)
         const HostTensor& wd = sd_get(sd, "conv" + S + "_" + J + "_down.weight");   // [21][32]
         const HostTensor& bdn = sd_get(sd, "conv" + S + "_" + J + "_down.bias");
@@ -552,7 +591,7 @@ struct Engine {
         Lt.e.mode = CONV_MSBLOCK;
         Lt.e.act = ACT_RELU;
         Lt.e.cout_store = 32;
-        Lt.e.o_hi = bd.o[s]->hi; Lt.e.o_lo = bd.o[s]->lo;
+        Lt.e.o_hi = o_buf->hi; Lt.e.o_lo = o_buf->lo; Lt.e.o_C = o_buf->C; Lt.e.o_coff = o_off;
         Lt.e.score_w = mem.upload(swv);
         Lt.e.score = bd.score[s];
         Lt.e.score_accum = j > 0;
@@ -584,7 +623,7 @@ struct Engine {
   void maxpool(const Act* src, const Act* dst, int stride, int batch, cudaStream_t st) {
     PoolParams p;
     p.src = make_view(*src, 0); p.dst = make_view(*dst, 0);
-    p.B = batch; p.Hi = src->H; p.Wi = src->W; p.Ho = dst->H; p.Wo = dst->W; p.stride = stride; p.Cv = src->C;
+    p.B = batch; p.Hi = src->H; p.Wi = src->W; p.Ho = dst->H; p.Wo = dst->W; p.stride = stride; p.Cv = dst->C;   // a merged source carries 32 more channels
     launch_1d(maxpool_kernel, p, (long long)batch * p.Ho * p.Wo * (p.Cv / 8), st);
     ++launches;
   }
@@ -605,8 +644,9 @@ struct Engine {
       aux("bdcn.first_conv", st, [&] { launch_first(fp, st); });
       static const int pool_after[13] = {-1, 0, -1, 1, -1, -1, 2, -1, -1, 3, -1, -1, -1};
       for (int i = 0; i < 13; ++i) {
-        if (i > 0) run_conv(bd.vgg[i], nb, st);
-        run_conv(bd.ms_in[i], nb, st);
+        if (i > 0 && !bd.merged[i - 1]) run_conv(bd.vgg[i], nb, st);
+        if (bd.merged[i]) run_conv(bd.vgg[i + 1], nb, st);       // features.conv(i+1) + msblock(i).conv in one launch
+        else run_conv(bd.ms_in[i], nb, st);
         run_conv(bd.ms_tail[i], nb, st);
         if (pool_after[i] >= 0)
           aux("bdcn.maxpool", st, [&] { maxpool(bd.f[i], bd.pool[pool_after[i]], pool_after[i] == 3 ? 1 : 2, nb, st); });
