@@ -101,6 +101,9 @@ struct ConvGeom {
   int ntaps, nchunks, groups; // groups: independent accumulators (1; 3 for the fused MSBlock tail)
   int cout_pad;               // weight rows per tap (multiple of 16)
   int kpad;                   // nchunks * EGN_KC
+  int phase;                  // tensor-core kernel only: d > 1 = the layer runs on the d x d polyphase lattice of its
+                              // input (H, W are the lattice sizes, batch counts frames x d*d phases, tap offsets are
+                              // in lattice units); a dilation-(k*d) 3x3 becomes a dilation-k 3x3 there
   int8_t tap_dy[EGN_MAX_TAPS], tap_dx[EGN_MAX_TAPS], tap_grp[EGN_MAX_TAPS];
   uint8_t chunk_src[EGN_MAX_CHUNKS];
   int16_t chunk_c0[EGN_MAX_CHUNKS];
@@ -126,6 +129,11 @@ struct ConvEpi {
   // optional InstanceNorm statistics of the stored values: stats[(n*stats_C + stats_coff + ch)*2 + {0: sum, 1: sum of squares}]
   double* stats;
   int stats_C, stats_coff;
+  // optional fused MaxPool2d(2, 2) (vgg16_c.py:15,20,27; even H and W): channels [0, pool_ch) of the stored map
+  // are also written, pooled, to a half-resolution buffer of pool_C channels (tensor-core kernel only)
+  bf16* pool_hi;
+  bf16* pool_lo;
+  int pool_C, pool_ch;
   // CONV_MSBLOCK: v = o + sum_g relu(acc_g + b_g); score[p][j] (+)= v . score_w[j]
   const bf16* o_hi;
   const bf16* o_lo;

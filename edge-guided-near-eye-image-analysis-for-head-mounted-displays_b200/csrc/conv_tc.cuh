@@ -45,6 +45,7 @@ struct TcParams {
   uint32_t a_plane_bytes, a_box_bytes, w_plane_bytes;
   int acc_bufs;                        // TMEM accumulator buffers (1 or 2)
   int n_aloads;
+  int a_C[EGN_MAX_SRC];                // channels of every source buffer
   int l2_prefetch;                     // producer prefetches its next tile's activation boxes into L2
   // upsample-add layers: the half-resolution operand patch of a tile ((tr/2 + 2) x (bw/2 + 2) pixels x n_tile
   // channels, both planes) is staged in shared memory by the epilogue warps with cp.async, one tile ahead
@@ -61,13 +62,14 @@ struct TcParams {
 // single-thread producer and MMA issuer never index kernel parameters dynamically (an indexed
 // constant-bank load costs hundreds of cycles on the issue path).
 struct TcTapStep { uint32_t a_off, d_col, flags, pad; };   // flags: 1 first tap of its box, 2 last tap of its box, 4 first tap of its accumulator group
-struct TcChunk { int src, c0, noff, pad; };
+struct TcChunk { int src, c0, noff, srcC; };   // srcC: channels of the source buffer (phase-lattice loads)
 struct TcLoad { int dx, tap0, ntaps, pad; };
 #define TC_SCHED_BYTES (32 * 16 + EGN_MAX_CHUNKS * 16 + TC_MAX_ALOADS * 16)
 
 #define TC_THREADS 320
 #define TC_EPI_WARPS 8
 #define TC_ACC_STRIDE 256   // TMEM columns between the two accumulator buffers
+#define TC_UP_PAIRS 6        // (pixel, 8-channel) pairs of the staged half-resolution patch per epilogue thread
 
 namespace tc {
 
@@ -127,6 +129,15 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint32_t bar, uint32_t dst,
+                                            int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 
@@ -209,17 +220,6 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
-}
-
-// 8 channels of one staged half-resolution pixel: hi plane at `a`, lo plane `plane` bytes further
-__device__ __forceinline__ void lds_px8(uint32_t a, uint32_t plane, float t[8]) {
-  const uint4 h = lds128(a), l = lds128(a + plane);
-  const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    t[2 * i] = __uint_as_float(hh[i] << 16) + __uint_as_float(ll[i] << 16);
-    t[2 * i + 1] = __uint_as_float(hh[i] & 0xffff0000u) + __uint_as_float(ll[i] & 0xffff0000u);
-  }
 }
 
 __device__ __forceinline__ bool elect_one() {
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   }
   if ((int)threadIdx.x >= 64 && (int)threadIdx.x < 64 + p.g.nchunks) {
     const int c = threadIdx.x - 64;
-    s_chunk[c] = TcChunk{(int)p.g.chunk_src[c], (int)p.g.chunk_c0[c], p.g.chunk_noff[c], 0};
+    s_chunk[c] = TcChunk{(int)p.g.chunk_src[c], (int)p.g.chunk_c0[c], p.g.chunk_noff[c], p.a_C[p.g.chunk_src[c]]};
   }
   if ((int)threadIdx.x >= 128 && (int)threadIdx.x < 128 + p.n_aloads) {
     const int l = threadIdx.x - 128;
@@ -445,9 +445,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int x0 = tx * bw;
         const int y0 = ty * p.tr - p.dmax;
         const int wrow0 = nb * n_tile;
+        // phase lattice: "frame" n is (image, row phase, column phase); the 5-D map addresses
+        // (phase_x * C + channel, lattice x, lattice y, phase_y, image)
+        const int phd = p.g.phase;
+        int n_img = n, ph_y = 0, ph_x = 0;
+        if (phd) { const int dd = phd * phd; n_img = n / dd; const int ph = n - n_img * dd; ph_y = ph / phd; ph_x = ph - ph_y * phd; }
         for (int c = 0; c < nchunks; ++c) {
           const TcChunk ck = s_chunk[c];
-          const int nn = n + ck.noff;
+          const int nn = n_img + ck.noff;
           const CUtensorMap* map_hi = &p.a_map[0][ck.src];
           const CUtensorMap* map_lo = &p.a_map[1][ck.src];
           for (int l = 0; l < n_aloads; ++l) {
@@ -460,8 +465,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               mbar_arrive(a_full(as));
             } else {
               mbar_expect_tx(a_full(as), a_tx);
-              tma_load_4d(map_hi, a_full(as), sA, ck.c0, x0 + ld.dx, y0, nn);
-              if (nplanes == 2) tma_load_4d(map_lo, a_full(as), sA + a_plane, ck.c0, x0 + ld.dx, y0, nn);
+              if (phd) {
+                tma_load_5d(map_hi, a_full(as), sA, ph_x * ck.srcC + ck.c0, x0 + ld.dx, y0, ph_y, nn);
+                if (nplanes == 2) tma_load_5d(map_lo, a_full(as), sA + a_plane, ph_x * ck.srcC + ck.c0, x0 + ld.dx, y0, ph_y, nn);
+              } else {
+                tma_load_4d(map_hi, a_full(as), sA, ck.c0, x0 + ld.dx, y0, nn);
+                if (nplanes == 2) tma_load_4d(map_lo, a_full(as), sA + a_plane, ck.c0, x0 + ld.dx, y0, nn);
+              }
             }
             if (++as == na) { as = 0; aph ^= 1u; }
             if (p.w_res) continue;
@@ -699,10 +709,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int mr = m >> p.bw_log2, mc = m & (bw - 1);
     int stat_flip = 0;
     int use = 0;
-    // upsample-add layers (decoder 1x1 convolutions): copies the (tr/2 + 2) x (bw/2 + 2) half-resolution pixels a
-    // tile blends (indices clamped like F.interpolate, align_corners=False) x n_tile channels x both planes
-    // into shared memory with cp.async, 16 bytes per request; issued one tile ahead so that the L2 / HBM
-    // latency hides behind the previous tile's epilogue instead of stalling this one
+    // upsample-add layers (decoder 1x1 convolutions): the (tr/2 + 2) x (bw/2 + 2) half-resolution pixels a tile
+    // blends (indices clamped like F.interpolate, align_corners=False) x n_tile channels are staged in shared
+    // memory one tile ahead: cp.async of the hi and lo 16-byte pieces (8 channels) side by side, which the SAME
+    // thread turns into 8 fp32 values in place once they have landed (up_convert) - the blend then reads plain
+    // fp32 and every half-resolution value is converted once instead of once per output pixel that uses it.
+    // Each thread owns up to TC_UP_PAIRS (pixel, 8-channel) pairs, fixed for the whole launch.
+    int up_desc[TC_UP_PAIRS];
+    int up_n = 0;
+    if (UP) {
+      const int c8n = p.n_tile >> 3;
+      const int npairs = p.up_rows * p.up_cols * c8n;
+#pragma unroll
+      for (int j = 0; j < TC_UP_PAIRS; ++j) {
+        const int i = (int)threadIdx.x - 64 + j * (TC_EPI_WARPS * 32);
+        up_desc[j] = 0;
+        if (i < npairs) {
+          const int c8 = i % c8n, pp = i / c8n;
+          up_desc[j] = (pp / p.up_cols) | ((pp % p.up_cols) << 8) | (c8 << 16);
+          up_n = j + 1;
+        }
+      }
+    }
     auto up_stage = [&](int t, int buf) {
       const int nb2 = t % p.n_blocks;
       int rest2 = t / p.n_blocks;
@@ -712,21 +740,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int n2 = rest2 / p.tiles_y;
       const int Hi = p.g.H >> 1, Wi = p.g.W >> 1;
       const int y0 = ((ty2 * p.tr) >> 1) - 1, x0 = ((tx2 * bw) >> 1) - 1;
-      const int c8n = p.n_tile >> 3;
-      const int per_plane = p.up_rows * p.up_cols * c8n;
       const uint32_t dst0 = up_base + (uint32_t)buf * p.up_patch_bytes;
       const size_t cbase = (size_t)p.e.up_coff + (size_t)nb2 * p.n_tile;
-      for (int i = (int)threadIdx.x - 64; i < 2 * per_plane; i += TC_EPI_WARPS * 32) {
-        const int plane = i >= per_plane ? 1 : 0;
-        int r = i - plane * per_plane;
-        const int c8 = r % c8n;
-        r /= c8n;
-        const int col = r % p.up_cols, row = r / p.up_cols;
-        const int yy = min(max(y0 + row, 0), Hi - 1), xx = min(max(x0 + col, 0), Wi - 1);
-        const bf16* src = (plane ? p.e.up_lo : p.e.up_hi) + (((size_t)n2 * Hi + yy) * Wi + xx) * p.e.up_C + cbase + c8 * 8;
-        cp_async16(dst0 + plane * p.up_plane_stride + (uint32_t)(row * p.up_cols + col) * p.up_pix_stride + c8 * 16, src);
+      const size_t fbase = (size_t)n2 * Hi * Wi;
+#pragma unroll
+      for (int j = 0; j < TC_UP_PAIRS; ++j) {
+        if (j < up_n) {
+          const int row = up_desc[j] & 255, col = (up_desc[j] >> 8) & 255, c8 = up_desc[j] >> 16;
+          const int yy = min(max(y0 + row, 0), Hi - 1), xx = min(max(x0 + col, 0), Wi - 1);
+          const size_t src = (fbase + (size_t)yy * Wi + xx) * p.e.up_C + cbase + c8 * 8;
+          const uint32_t dst = dst0 + (uint32_t)(row * p.up_cols + col) * p.up_pix_stride + c8 * 32;
+          cp_async16(dst, p.e.up_hi + src);
+          cp_async16(dst + 16, p.e.up_lo + src);
+        }
       }
       cp_async_commit();
+    };
+    auto up_convert = [&](int buf) {
+      const uint32_t dst0 = up_base + (uint32_t)buf * p.up_patch_bytes;
+#pragma unroll
+      for (int j = 0; j < TC_UP_PAIRS; ++j) {
+        if (j < up_n) {
+          const int row = up_desc[j] & 255, col = (up_desc[j] >> 8) & 255, c8 = up_desc[j] >> 16;
+          const uint32_t dst = dst0 + (uint32_t)(row * p.up_cols + col) * p.up_pix_stride + c8 * 32;
+          const uint4 h = lds128(dst), l = lds128(dst + 16);
+          const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+          uint32_t f[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            f[2 * i] = __float_as_uint(__uint_as_float(hh[i] << 16) + __uint_as_float(ll[i] << 16));
+            f[2 * i + 1] = __float_as_uint(__uint_as_float(hh[i] & 0xffff0000u) + __uint_as_float(ll[i] & 0xffff0000u));
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(f[0]), "r"(f[1]), "r"(f[2]), "r"(f[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16), "r"(f[4]), "r"(f[5]), "r"(f[6]), "r"(f[7]) : "memory");
+        }
+      }
     };
     if (UP && (int)blockIdx.x < p.total_tiles) up_stage(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++use) {
@@ -741,6 +789,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t aphase = (p.acc_bufs == 2 ? (use >> 1) : use) & 1u;
       const int px = tx * bw + mc;
 
+      // fused MSBlock tail with wide MMAs (phase lattice): this warp owns 16 of the 32 channels of its 32 pixels;
+      // `o` and the running score are requested before the accumulator is awaited
+      const bool tail2 = !UP && p.e.mode == CONV_MSBLOCK && p.wide_b;
+      int n_img = n, ph_y = 0, ph_x = 0, phd = 1;
+      if (!UP && p.g.phase) {
+        phd = p.g.phase;
+        const int dd = phd * phd;
+        n_img = n / dd;
+        const int ph = n - n_img * dd;
+        ph_y = ph / phd; ph_x = ph - ph_y * phd;
+      }
+      auto tail_pix = [&](int s, bool& valid) -> size_t {
+        const int qy = ty * p.tr + s * p.sr + mr;
+        valid = (qy < p.g.H) && (px < p.g.W);
+        return ((size_t)n_img * (p.g.H * phd) + (qy * phd + ph_y)) * (size_t)(p.g.W * phd) + (px * phd + ph_x);
+      };
+      float o_pre[16];
+      float2 sc_pre = make_float2(0.f, 0.f);
+      if (tail2) {
+        bool valid;
+        const size_t pix = tail_pix(0, valid);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o_pre[i] = 0.f;
+        if (valid) {
+          load16(p.e.o_hi, p.e.o_lo, pix * p.e.o_C + p.e.o_coff + (half << 4), o_pre);
+          if (half == 0 && p.e.score_accum) sc_pre = reinterpret_cast<const float2*>(p.e.score)[pix];
+        }
+      }
       mbar_wait(tfull_bar(ab), aphase, p.err_flag, 6);
       fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * TC_ACC_STRIDE;
@@ -748,6 +824,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // this tile's half-resolution patch has landed (everybody's copies), and everybody is done reading the
         // other buffer (they are past the previous tile): refill it with the next tile's patch
         cp_async_wait_all();
+        up_convert(use & 1);
         asm volatile("bar.sync 3, 256;" ::: "memory");
         if (tile + (int)gridDim.x < p.total_tiles) up_stage(tile + gridDim.x, (use + 1) & 1);
       }
@@ -806,21 +883,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                   const int ca = min(xa - x0, p.up_cols - 1), cc = min(xb - x0, p.up_cols - 1);
                   const float wya = (py & 1) ? 0.75f : 0.25f, wyb = 1.f - wya;
                   const float wxa = (px & 1) ? 0.75f : 0.25f, wxb = 1.f - wxa;
-                  const uint32_t chb = up_buf + (uint32_t)c0 * 2u;
+                  const float w00 = wya * wxa, w01 = wya * wxb, w10 = wyb * wxa, w11 = wyb * wxb;   // exact (multiples of 1/16)
+                  const uint32_t chb = up_buf + (uint32_t)c0 * 4u;
                   const uint32_t a00 = chb + (uint32_t)(ra * p.up_cols + ca) * p.up_pix_stride, a01 = chb + (uint32_t)(ra * p.up_cols + cc) * p.up_pix_stride;
                   const uint32_t a10 = chb + (uint32_t)(rb * p.up_cols + ca) * p.up_pix_stride, a11 = chb + (uint32_t)(rb * p.up_cols + cc) * p.up_pix_stride;
 #pragma unroll
-                  for (int h8 = 0; h8 < 2; ++h8) {
-                    float t00[8], t01[8], t10[8], t11[8];
-                    lds_px8(a00 + h8 * 16, p.up_plane_stride, t00);
-                    lds_px8(a01 + h8 * 16, p.up_plane_stride, t01);
-                    lds_px8(a10 + h8 * 16, p.up_plane_stride, t10);
-                    lds_px8(a11 + h8 * 16, p.up_plane_stride, t11);
+                  for (int q4 = 0; q4 < 4; ++q4) {
+                    const uint4 t00 = lds128(a00 + q4 * 16), t01 = lds128(a01 + q4 * 16), t10 = lds128(a10 + q4 * 16), t11 = lds128(a11 + q4 * 16);
+                    const uint32_t e00[4] = {t00.x, t00.y, t00.z, t00.w}, e01[4] = {t01.x, t01.y, t01.z, t01.w};
+                    const uint32_t e10[4] = {t10.x, t10.y, t10.z, t10.w}, e11[4] = {t11.x, t11.y, t11.z, t11.w};
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                      const int i = h8 * 8 + k;
-                      const float top = wxa * t00[k] + wxb * t01[k], bot = wxa * t10[k] + wxb * t11[k];
-                      v[i] = apply_act((__uint_as_float(r[u][i]) + bias[i]) + (wya * top + wyb * bot), p.e.act);
+                    for (int k = 0; k < 4; ++k) {
+                      const int i = q4 * 4 + k;
+                      const float up = fmaf(w00, __uint_as_float(e00[k]), fmaf(w01, __uint_as_float(e01[k]),
+                                       fmaf(w10, __uint_as_float(e10[k]), w11 * __uint_as_float(e11[k]))));
+                      v[i] = apply_act((__uint_as_float(r[u][i]) + bias[i]) + up, p.e.act);
                     }
                   }
                 } else {
@@ -839,6 +916,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                       if (i < p.e.logits_c) dst[(size_t)i * p.g.H * p.g.W] = v[i];
                   }
                 } else if (valid) store16(p.e.out_hi, p.e.out_lo, pix * p.e.out_C + p.e.out_coff + cb, v);
+                if (!UP && p.e.pool_hi && cb < p.e.pool_ch) {
+                  // fused 2x2 / stride 2 max-pool: the window partners are lanes ^1 (x) and ^bw (y) of this warp (tile
+                  // origins are even, H and W are even, so a window is entirely valid or entirely outside the frame);
+                  // rounding is monotonic, so pooling before the split equals pooling the stored hi + lo values
+                  float m[16];
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    const float a = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
+                    m[i] = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, bw));
+                  }
+                  if (valid && !((mc | mr) & 1)) {
+                    const size_t pp = ((size_t)n * (p.g.H >> 1) + (py >> 1)) * (size_t)(p.g.W >> 1) + (px >> 1);
+                    store16(p.e.pool_hi, p.e.pool_lo, pp * p.e.pool_C + cb, m);
+                  }
+                }
                 if (p.e.stats) {
                   const float mk = valid ? 1.f : 0.f;
 #pragma unroll
@@ -865,6 +957,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
             ++stat_flip;
           }
+        }
+      } else if (tail2) {
+        // fused MSBlock tail (bdcn_new.py:49-55 + conv*_down/score_dsn* collapsed), wide layout: group g
+        // holds hi*hi + lo*hi in columns [64 g, 64 g + 32) and hi*lo in [64 g + 32, 64 g + 64) of every sub-tile.
+        // The two warps of a lane quarter split the 32 channels; the upper half hands its two partial dots
+        // to the lower one through shared memory (double-buffered by tile parity).
+        const int c0 = half << 4;
+        for (int s = 0; s < nsub; ++s) {
+          bool valid;
+          const size_t pix = tail_pix(s, valid);
+          float v[16];
+          float2 sc = sc_pre;
+          if (s == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = o_pre[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            sc = make_float2(0.f, 0.f);
+            if (valid) {
+              load16(p.e.o_hi, p.e.o_lo, pix * p.e.o_C + p.e.o_coff + c0, v);
+              if (half == 0 && p.e.score_accum) sc = reinterpret_cast<const float2*>(p.e.score)[pix];
+            }
+          }
+          const uint32_t tb = tbase + (uint32_t)s * (uint32_t)(p.g.groups * 64);
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            uint32_t r[16], q[16];
+            tmem_ld16(tb + g * 64 + c0, r);
+            tmem_ld16(tb + g * 64 + 32 + c0, q);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              v[i] += fmaxf((__uint_as_float(r[i]) + __uint_as_float(q[i])) + c_bias[g * p.g.cout_pad + c0 + i], 0.f);
+          }
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            s0 = fmaf(v[i], c_scale[c0 + i], s0);
+            s1 = fmaf(v[i], c_scale[32 + c0 + i], s1);
+          }
+          float2* xb = reinterpret_cast<float2*>(stat_buf) + ((stat_flip & 1) * 4 + quarter) * 32 + lane;
+          if (half == 1) *xb = make_float2(s0, s1);
+          asm volatile("bar.sync %0, 64;" ::"r"(4 + quarter) : "memory");
+          if (half == 0 && valid) {
+            const float2 o2 = *xb;
+            sc.x += s0 + o2.x;
+            sc.y += s1 + o2.y;
+            reinterpret_cast<float2*>(p.e.score)[pix] = sc;
+          }
+          ++stat_flip;
         }
       } else {
         // fused MSBlock tail (bdcn_new.py:49-55 + conv*_down/score_dsn* collapsed)
@@ -966,6 +1109,22 @@ static void make_act_map(CUtensorMap* map, const bf16* ptr, int N, int H, int W,
   EGN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
 }
 
+// 5-D map over the d x d polyphase lattice of an NHWC bf16 plane: pixel (y, x) = (yq * d + yp, xq * d + xp), so
+// address = n*H*W*C + yq*(d*W*C) + yp*(W*C) + xq*(d*C) + (xp*C + c): dims (d*C, W/d, H/d, d, N), box (32, bw, rows, 1, 1).
+// A box is then a dense window of ONE phase; out-of-bounds lattice coordinates zero-fill like the padding of the
+// dilated convolution.  Needs H % d == 0 and W % d == 0.
+static void make_act_map_phase(CUtensorMap* map, const bf16* ptr, int N, int H, int W, int C, int d, int box_w, int box_rows) {
+  EGN_CHECK(H % d == 0 && W % d == 0, "phase lattice needs H and W divisible by the phase");
+  cuuint64_t dims[5] = {(cuuint64_t)d * C, (cuuint64_t)(W / d), (cuuint64_t)(H / d), (cuuint64_t)d, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)d * C * 2, (cuuint64_t)d * W * C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[5] = {EGN_KC, (cuuint32_t)box_w, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)ptr, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EGN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(phase lattice) failed: " + std::to_string((int)r));
+}
+
 // 2-D map over the packed weights [rows = ntaps*cout_pad][kpad], box (32, n_tile).
 static void make_w_map(CUtensorMap* map, const bf16* ptr, int rows, int kpad, int n_tile) {
   cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)rows};
@@ -1010,10 +1169,12 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
     ndx = ns;
   }
   p.xshare = (ndx > 1 && dxmax <= 2 && dymax <= 2 && g.groups == 1 && !getenv("EGN_TC_NO_XSHARE")) ? 1 : 0;
+  // MSBlock tail on the phase lattice: dilations 4/8/12 are 1/2/3 there and ONE (8 + 6) x (16 + 6) box serves all 27 taps
+  if (g.phase) { EGN_CHECK(dxmax <= 3 && dymax <= 3, "phase lattice: tap offsets beyond 3"); p.xshare = 1; }
   p.dxmax = dxmax;
   // sub-tile shape: 8 rows x 16 px or 16 rows x 8 px, whichever covers the frame with less padding
   auto padded = [&](int bw) { const int sr = 128 / bw; return (long long)round_up(g.W, bw) * round_up(g.H, sr); };
-  if (padded(8) > padded(16)) p.xshare = 0;      // 120x160: 16-row sub-tiles would waste 6.7 % of the MMAs
+  if (padded(8) > padded(16) && !g.phase) p.xshare = 0;      // 120x160: 16-row sub-tiles would waste 6.7 % of the MMAs
   const int bw = p.xshare ? 8 : (padded(8) < padded(16) ? 8 : 16);
   p.bw_log2 = bw == 8 ? 3 : 4;
   p.sr = 128 / bw;
@@ -1033,6 +1194,7 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   // M=128, N<=64 MMA takes (128+N)/4 cycles, tools/mma_probe.cu): fold hi*hi and hi*lo into one MMA
   p.wide_b = (nsplit == 3 && g.groups == 1 && p.n_tile <= 64) ? 1 : 0;
   if (const char* e = getenv("EGN_TC_WIDE")) p.wide_b = atoi(e) ? p.wide_b : 0;
+  if (g.phase) { EGN_CHECK(nsplit == 3 && g.groups == 3 && p.n_tile == 32, "phase lattice is the MSBlock tail's layout"); p.wide_b = 1; }
   const int cols = g.groups * p.n_tile * (p.wide_b ? 2 : 1);
   EGN_CHECK(cols <= 512, "accumulator groups exceed TMEM");
   // more sub-tiles per CTA tile amortise the weight stream and give the MMA pipe independent
@@ -1086,9 +1248,10 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   p.up_rows = p.up_cols = 0; p.up_pix_stride = p.up_plane_stride = p.up_patch_bytes = 0;
   if (p.e.up_hi) {
     p.up_rows = p.tr / 2 + 2; p.up_cols = (1 << p.bw_log2) / 2 + 2;
-    p.up_pix_stride = (uint32_t)p.n_tile * 2u + 16u;
-    p.up_plane_stride = (uint32_t)(p.up_rows * p.up_cols) * p.up_pix_stride;
-    p.up_patch_bytes = 2u * p.up_plane_stride;
+    p.up_pix_stride = (uint32_t)p.n_tile * 4u + 16u;           // 8 channels = hi 16 B | lo 16 B, converted in place to 8 fp32
+    p.up_plane_stride = 0;
+    p.up_patch_bytes = (uint32_t)(p.up_rows * p.up_cols) * p.up_pix_stride;
+    EGN_CHECK(p.up_rows * p.up_cols * (p.n_tile / 8) <= TC_UP_PAIRS * TC_EPI_WARPS * 32, "upsample patch exceeds the staging slots");
   }
   const size_t budget = 227 * 1024 - 1024 - 512 - 2048 - 7168 - TC_SCHED_BYTES - (p.e.up_hi ? 2 * (size_t)p.up_patch_bytes + 16 : 0);
   const size_t a_slot = (size_t)nplanes * p.a_plane_bytes, w_slot = (size_t)nplanes * p.w_plane_bytes;
@@ -1107,7 +1270,7 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   p.w_res = 0;
   {
     const size_t all_w = w_slot * (size_t)g.ntaps * g.nchunks;
-    if (p.n_blocks == 1 && all_w <= 48 * 1024 && budget >= 2 * a_slot + all_w && !getenv("EGN_TC_NO_WRES")) {
+    if (p.n_blocks == 1 && (all_w <= 48 * 1024 || g.phase) && budget >= 2 * a_slot + all_w && !getenv("EGN_TC_NO_WRES")) {
       p.w_res = 1; p.w_box = 1; p.w_slot_taps = g.ntaps * g.nchunks;
     }
   }

@@ -378,7 +378,8 @@ int egn_conv_selfcheck(egn_ctx* ctx, const char* layer, int frames, double* max_
     L.tc.e.logits = logits_scratch; L.simt.e.logits = logits_scratch;
   }
   TcParams tp = L.tc;
-  tp.g.batch = n; tp.total_tiles = tp.tiles_x * tp.tiles_y * n * tp.n_blocks; tp.e.score_accum = 0;
+  tp.g.batch = n * (L.phase ? L.phase * L.phase : 1);
+  tp.total_tiles = tp.tiles_x * tp.tiles_y * tp.g.batch * tp.n_blocks; tp.e.score_accum = 0;
   tc_launch(tp, e.num_sms, 0);
   fetch(a);
   SimtParams sp = L.simt;

@@ -112,6 +112,7 @@ struct ConvLayer {
   int cout = 0;
   TcParams tc{};
   SimtParams simt{};
+  int phase = 0;         // tensor-core path runs on the phase x phase polyphase lattice of its input (MSBlock tails, stages 1-2)
   double flops = 0;      // algorithmic 2*MAC at unpadded sizes, per frame
   double prof_ms = 0;    // accumulated kernel time (profiling mode)
   double prof_frames = 0;
@@ -148,6 +149,7 @@ struct Engine {
     const float *first_w_gray, *first_w_rgb;
     ConvLayer vgg[13];           // index 0 unused (first_conv)
     ConvLayer ms_in[13], ms_tail[13];
+    bool pool_fused[4];          // pool k (2x2 / stride 2) is written by the epilogue of the convolution that produces its input
     bool merged[13];             // merged[i]: msblock i's `conv` rides as 32 extra output channels of vgg[i + 1] (same input map)
     int f_c[13];                 // VGG channels of f[i] (a merged f[i] buffer holds 32 more: the MSBlock's `o`)
     BdcnTailParams tail;
@@ -341,9 +343,26 @@ struct Engine {
     // tensor-core parameters
     L.tc.g = L.g; L.tc.e = L.e; L.tc.err_flag = err_flag; L.tc.timing = nullptr;
     if (use_tc) {
+      if (L.phase) {
+        // same taps and weights on the polyphase lattice: H/d x W/d "frames", d*d of them per image
+        const int d = L.phase;
+        ConvGeom& tg = L.tc.g;
+        EGN_CHECK(tg.H % d == 0 && tg.W % d == 0, L.name + ": phase lattice needs divisible sizes");
+        tg.phase = d; tg.H /= d; tg.W /= d; tg.batch *= d * d;
+        for (int t = 0; t < tg.ntaps; ++t) {
+          EGN_CHECK(tg.tap_dy[t] % d == 0 && tg.tap_dx[t] % d == 0, L.name + ": tap offsets must be multiples of the phase");
+          tg.tap_dy[t] = (int8_t)(tg.tap_dy[t] / d); tg.tap_dx[t] = (int8_t)(tg.tap_dx[t] / d);
+        }
+      }
       tc_configure(L.tc, L.g.cout_pad, nsplit);
+      for (int s = 0; s < L.nsrc; ++s) L.tc.a_C[s] = L.src_act[s]->C;
       for (int s = 0; s < L.nsrc; ++s) {
         const Act* a = L.src_act[s];
+        if (L.phase) {
+          make_act_map_phase(&L.tc.a_map[0][s], a->hi, a->N, a->H, a->W, a->C, L.phase, L.tc.box_w, L.tc.box_rows);
+          make_act_map_phase(&L.tc.a_map[1][s], a->lo, a->N, a->H, a->W, a->C, L.phase, L.tc.box_w, L.tc.box_rows);
+          continue;
+        }
         // channel window of this source the layer reads: [lo, hi) in 64-byte chunks
         int lo = a->C, hi = 0;
         for (int c = 0; c < L.g.nchunks; ++c)
@@ -379,10 +398,10 @@ struct Engine {
   void run_conv_impl(ConvLayer& L, int batch, cudaStream_t st, int noff = -1) {
     if (use_tc) {
       TcParams p = L.tc;
-      p.g.batch = batch;
+      p.g.batch = batch * (L.phase ? L.phase * L.phase : 1);
       if (noff >= 0)
         for (int c = 0; c < p.g.nchunks; ++c) if (p.g.chunk_noff[c]) p.g.chunk_noff[c] = noff;
-      p.total_tiles = p.tiles_x * p.tiles_y * batch * p.n_blocks;
+      p.total_tiles = p.tiles_x * p.tiles_y * p.g.batch * p.n_blocks;
       tc_launch(p, num_sms, st);
       ++launches;
     } else {
@@ -540,6 +559,17 @@ struct Engine {
       set_store_epilogue(bd.vgg[i], bd.f[i], 0, ACT_RELU);
       finalize_conv(bd.vgg[i]);
     }
+    // pools 1-3 (2x2 / stride 2 on even sizes) ride in the producing convolution's epilogue; pool4 (stride 1) stays a kernel
+    {
+      static const int src_of_pool[3] = {1, 3, 6};
+      const bool fuse = use_tc && !getenv("EGN_NO_POOL_FUSE");
+      for (int k = 0; k < 4; ++k) bd.pool_fused[k] = false;
+      for (int k = 0; k < 3 && fuse; ++k) {
+        ConvLayer& L = bd.vgg[src_of_pool[k]];
+        L.tc.e.pool_hi = bd.pool[k]->hi; L.tc.e.pool_lo = bd.pool[k]->lo; L.tc.e.pool_C = bd.pool[k]->C; L.tc.e.pool_ch = cout[src_of_pool[k]];
+        bd.pool_fused[k] = true;
+      }
+    }
     // MSBlocks + collapsed side chain
     static const int nblk[5] = {2, 2, 3, 3, 3};
     const HostTensor& fw = sd_get(sd, "fuse.weight");
@@ -596,6 +626,10 @@ struct Engine {
         Lt.e.score = bd.score[s];
         Lt.e.score_accum = j > 0;
         Lt.flops += 2.0 * 32 * 21 * sh[s] * sw_[s];      // conv_down (the reference's 1x1)
+        // stages 1-2 (240x320, 120x160): run on the 4x4 polyphase lattice, where the three dilations are 1/2/3, one
+        // shared activation box serves all 27 taps and the weights stay resident (conv_tc.cuh)
+        static const int tail_phase = getenv("EGN_TAIL_PHASE") ? atoi(getenv("EGN_TAIL_PHASE")) : 4;
+        Lt.phase = (use_tc && nsplit == 3 && s <= 1 && tail_phase > 1) ? tail_phase : 0;
         finalize_conv(Lt);
       }
       bd.tail.cA[s] = (float)cA; bd.tail.cB[s] = (float)cB;
@@ -648,7 +682,7 @@ struct Engine {
         if (bd.merged[i]) run_conv(bd.vgg[i + 1], nb, st);       // features.conv(i+1) + msblock(i).conv in one launch
         else run_conv(bd.ms_in[i], nb, st);
         run_conv(bd.ms_tail[i], nb, st);
-        if (pool_after[i] >= 0)
+        if (pool_after[i] >= 0 && !bd.pool_fused[pool_after[i]])
           aux("bdcn.maxpool", st, [&] { maxpool(bd.f[i], bd.pool[pool_after[i]], pool_after[i] == 3 ? 1 : 2, nb, st); });
       }
       BdcnTailParams tp = bd.tail;
