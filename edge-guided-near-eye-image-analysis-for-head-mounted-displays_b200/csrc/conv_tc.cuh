@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
       }
       if (ptm) {
-        long long* o = p.timing + (size_t)blockIdx.x * 10;
+        long long* o = p.timing + (size_t)blockIdx.x * 12;
         o[6] = ptm_a; o[7] = ptm_w; o[8] = clock64() - ptm_start;
       }
     }
@@ -542,18 +542,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       uint32_t aph = 0, wph = 0;
       int use = 0;                                   // tiles issued so far by this CTA
       const bool tm = p.timing != nullptr;
-      long long tm_te = 0, tm_a = 0, tm_w = 0, tm_i = 0, tm_k = 0, tm_c0 = 0;
+      long long tm_te = 0, tm_a = 0, tm_w = 0, tm_i = 0, tm_k = 0, tm_c0 = 0, tm_x = 0, tm_h = 0, tm_l = 0;
       const long long tm_start = tm ? clock64() : 0;
       if (p.w_res) {
         mbar_wait(w_full(0), 0u, p.err_flag, 5);
         fence_after();
       }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++use) {
+        if (tm) tm_l = clock64();
         const int ty = (tile / (p.n_blocks * p.tiles_x)) % p.tiles_y;
         const int nsub = min(p.S, (p.g.H - ty * p.tr + p.sr - 1) / p.sr);
         const int ab = p.acc_bufs == 2 ? (use & 1) : 0;
         const uint32_t aphase = (p.acc_bufs == 2 ? (use >> 1) : use) & 1u;
-        if (tm) tm_c0 = clock64();
+        if (tm) { tm_c0 = clock64(); tm_h += tm_c0 - tm_l; }
         mbar_wait(tempty_bar(ab), aphase ^ 1u, p.err_flag, 3);
         if (tm) tm_te += clock64() - tm_c0;
         fence_after();
@@ -691,13 +692,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           else if (nsub == 3) run_tile(I3{}, I1{}, I0{});
           else run_tile(I1{}, I1{}, I0{});
         }
+        if (tm) tm_l = clock64();
         if (elect_one()) mma_commit(tfull_bar(ab));  // accumulators complete -> epilogue
         __syncwarp();
+        if (tm) tm_x += clock64() - tm_l;
       }
       if (tm) {
         // counters are summed over lanes by the elected thread only for tm_i / tm_k
-        long long* o = p.timing + (size_t)blockIdx.x * 10;
-        if (lane == 0) { o[0] = clock64() - tm_start; o[1] = tm_te; o[2] = tm_a; o[3] = tm_w; o[5] = use; }
+        long long* o = p.timing + (size_t)blockIdx.x * 12;
+        if (lane == 0) { o[0] = clock64() - tm_start; o[1] = tm_te; o[2] = tm_a; o[3] = tm_w; o[5] = use; o[10] = tm_x; o[11] = tm_h; }
         if (tm_i) { o[4] = tm_i; o[9] = tm_k; }
       }
     }
@@ -1297,20 +1300,20 @@ static void tc_launch(const TcParams& p, int num_sms, cudaStream_t stream) {
   if (timing) {
     // debugging aid: per-role cycle counters of one launch, averaged over CTAs, to stderr
     static long long* buf = nullptr;
-    if (!buf) CUDA_OK(cudaMalloc(&buf, 148 * 10 * sizeof(long long)));
-    CUDA_OK(cudaMemsetAsync(buf, 0, 148 * 10 * sizeof(long long), stream));
+    if (!buf) CUDA_OK(cudaMalloc(&buf, 148 * 12 * sizeof(long long)));
+    CUDA_OK(cudaMemsetAsync(buf, 0, 148 * 12 * sizeof(long long), stream));
     TcParams q = p;
     q.timing = buf;
     if (q.e.up_hi) conv_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(q);
     else conv_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(q);
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(stream));
-    long long h[148 * 10];
+    long long h[148 * 12];
     CUDA_OK(cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost));
-    double a[10] = {0};
-    for (int b = 0; b < grid; ++b) for (int k = 0; k < 10; ++k) a[k] += (double)h[b * 10 + k] / grid;
-    fprintf(stderr, "tc_timing H=%d W=%d chunks=%d taps=%d ntile=%d S=%d na=%d nw=%d batch=%d | mma: total %.0f tempty %.0f a_full %.0f w_full %.0f issue %.0f commit %.0f tiles %.1f | prod: a_empty %.0f w_empty %.0f total %.0f\n",
-            p.g.H, p.g.W, p.g.nchunks, p.g.ntaps, p.n_tile, p.S, p.na, p.nw, p.g.batch, a[0], a[1], a[2], a[3], a[4], a[9], a[5], a[6], a[7], a[8]);
+    double a[12] = {0};
+    for (int b = 0; b < grid; ++b) for (int k = 0; k < 12; ++k) a[k] += (double)h[b * 12 + k] / grid;
+    fprintf(stderr, "tc_timing H=%d W=%d chunks=%d taps=%d ntile=%d S=%d na=%d nw=%d batch=%d | mma: total %.0f tempty %.0f a_full %.0f w_full %.0f issue %.0f commit %.0f tfullcommit %.0f head %.0f tiles %.1f | prod: a_empty %.0f w_empty %.0f total %.0f\n",
+            p.g.H, p.g.W, p.g.nchunks, p.g.ntaps, p.n_tile, p.S, p.na, p.nw, p.g.batch, a[0], a[1], a[2], a[3], a[4], a[9], a[10], a[11], a[5], a[6], a[7], a[8]);
     return;
   }
   if (p.e.up_hi) conv_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(p);
