@@ -22,8 +22,11 @@ struct SimtParams {
 #define ST_THREADS 256
 
 __global__ void __launch_bounds__(ST_THREADS) conv_simt_kernel(const SimtParams p) {
-  __shared__ float sA[ST_PX][EGN_KC + 1];
-  __shared__ float sW[ST_CO][EGN_KC + 1];
+  // hi and lo parts are kept apart and multiplied like the tensor-core kernel does (hi*hi + lo*hi + hi*lo, the
+  // lo*lo term is dropped): the cross-check then holds for ANY buffer contents, also for stale planes of a
+  // shared workspace region whose "lo" is not small against its "hi"
+  __shared__ float sA[ST_PX][EGN_KC + 1], sAl[ST_PX][EGN_KC + 1];
+  __shared__ float sW[ST_CO][EGN_KC + 1], sWl[ST_CO][EGN_KC + 1];
   __shared__ float sRed[ST_PX][4][2];
   const int HW = p.g.H * p.g.W;
   const int tiles_per_frame = (HW + ST_PX - 1) / ST_PX;
@@ -50,34 +53,37 @@ __global__ void __launch_bounds__(ST_THREADS) conv_simt_kernel(const SimtParams 
       for (int e = t; e < ST_PX * EGN_KC; e += ST_THREADS) {
         const int q = e / EGN_KC, k = e % EGN_KC;
         const int lin = p0 + q;
-        float v = 0.f;
+        float v = 0.f, vl = 0.f;
         if (lin < HW) {
           const int y = lin / p.g.W + p.g.tap_dy[tap], x = lin % p.g.W + p.g.tap_dx[tap];
           const int cc = c0 + k;
           if (y >= 0 && y < p.g.H && x >= 0 && x < p.g.W && cc < s.C) {   // TMA zero-fills the rest
             const size_t a = (((size_t)(n + p.g.chunk_noff[c]) * p.g.H + y) * p.g.W + x) * s.C + cc;
             v = __bfloat162float(s.hi[a]);
-            if (p.nsplit != 1) v += __bfloat162float(s.lo[a]);
+            if (p.nsplit != 1) vl = __bfloat162float(s.lo[a]);
           }
         }
-        sA[q][k] = v;
+        sA[q][k] = v; sAl[q][k] = vl;
       }
       for (int e = t; e < ST_CO * EGN_KC; e += ST_THREADS) {
         const int co = e / EGN_KC, k = e % EGN_KC;
-        float v = 0.f;
+        float v = 0.f, vl = 0.f;
         if (cb + co < p.g.cout_pad) {
           const size_t w = ((size_t)tap * p.g.cout_pad + cb + co) * p.g.kpad + c * EGN_KC + k;
           v = __bfloat162float(p.w_hi[w]);
-          if (p.nsplit != 1) v += __bfloat162float(p.w_lo[w]);
+          if (p.nsplit != 1) vl = __bfloat162float(p.w_lo[w]);
         }
-        sW[co][k] = v;
+        sW[co][k] = v; sWl[co][k] = vl;
       }
       __syncthreads();
 #pragma unroll 8
       for (int k = 0; k < EGN_KC; ++k) {
-        const float a = sA[px][k];
+        const float a = sA[px][k], al = sAl[px][k];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) cur[i] = fmaf(a, sW[cog * 8 + i][k], cur[i]);
+        for (int i = 0; i < 8; ++i) {
+          const float wh = sW[cog * 8 + i][k];
+          cur[i] = fmaf(a, wh, fmaf(al, wh, fmaf(a, sWl[cog * 8 + i][k], cur[i])));
+        }
       }
     }
     const int grp = p.g.tap_grp[tap];

@@ -59,6 +59,7 @@ int egn_create(int device, const egn_config* cfg, egn_ctx** out) {
   std::unique_ptr<egn_ctx> c(new egn_ctx());
   c->eng.device = device;
   c->eng.num_sms = prop.multiProcessorCount;
+  if (const char* ns = getenv("EGN_NUM_SMS")) c->eng.num_sms = std::max(1, std::min(atoi(ns), prop.multiProcessorCount));   // tuning knob: persistent-grid cap
   c->eng.cfg.add_edge = cfg->add_edge; c->eng.cfg.add_seg = cfg->add_seg;
   c->eng.cfg.seg_detach = cfg->seg_detach; c->eng.cfg.input_concat = cfg->input_concat;
   c->eng.cfg.only_edge = cfg->only_edge; c->eng.cfg.style_dim = cfg->style_dim;
@@ -107,7 +108,7 @@ int egn_set_weights(egn_ctx* ctx, int net, const void* blob, size_t bytes) {
 int egn_plan(egn_ctx* ctx, int micro_batch) {
   API_BEGIN
   EGN_CHECK(ctx, "null context");
-  EGN_CHECK(micro_batch >= 1 && micro_batch <= 256, "micro_batch must be in [1,256]");
+  EGN_CHECK(micro_batch >= 1 && micro_batch <= 1024, "micro_batch must be in [1,1024]");
   EGN_CHECK(!ctx->eng.built_bdcn && !ctx->eng.built_esf, "plan must precede the first forward");
   ctx->eng.mb = micro_batch;
   API_END

@@ -201,15 +201,69 @@ struct Engine {
     CUDA_OK(cudaFuncSetAttribute(head_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_TAIL_SMEM));
   }
 
-  Act* new_act(DevMem& mem, int N, int H, int W, int C) {
+  // ---- liveness-planned workspace.  Every split-bf16 activation declares the interval [t0, t1] of the forward
+  // schedule (ticks, see build_bdcn / build_esf) in which it is live; commit_acts packs the planes of a net into ONE
+  // allocation so that buffers with disjoint intervals share memory (largest first, lowest offset that is free
+  // for the whole interval).  Sharing is safe because (1) every plane holds bf16 values written by our own
+  // kernels or zeros, so a K chunk that over-reads into a not-yet-written window meets finite numbers times
+  // zero weights, and (2) a context runs its forwards in stream order.  Buffers that rely on channels nobody
+  // ever writes staying zero are declared with t0 = 0, t1 = INT_MAX (never shared).  EGN_NO_ARENA=1 gives every
+  // buffer its own allocation (tools/gpu_debug.py reads intermediate maps after the forward).
+  struct ActReq { Act* act; int t0, t1; size_t off_hi, off_lo; };
+  std::vector<ActReq> pending_acts;
+  size_t arena_bytes = 0, arena_naive_bytes = 0;
+
+  Act* new_act(DevMem& mem, int N, int H, int W, int C, int t0 = 0, int t1 = 0x7fffffff) {
     EGN_CHECK(C % 8 == 0, "Act channels must be a multiple of 8");
     std::unique_ptr<Act> a(new Act());
     a->N = N; a->H = H; a->W = W; a->C = C;
-    const size_t bytes = a->plane_elems() * sizeof(bf16);
-    a->hi = (bf16*)mem.alloc(bytes);
-    a->lo = (bf16*)mem.alloc(bytes);
+    static const bool no_arena = getenv("EGN_NO_ARENA") != nullptr;
+    if (no_arena) {
+      const size_t bytes = a->plane_elems() * sizeof(bf16);
+      a->hi = (bf16*)mem.alloc(bytes);
+      a->lo = (bf16*)mem.alloc(bytes);
+    } else {
+      pending_acts.push_back({a.get(), t0, t1, 0, 0});
+    }
     acts.push_back(std::move(a));
     return acts.back().get();
+  }
+
+  void commit_acts(DevMem& mem) {
+    if (pending_acts.empty()) return;
+    struct Item { size_t bytes; int t0, t1; size_t off; bool placed; };
+    std::vector<Item> items;
+    for (auto& r : pending_acts) {
+      const size_t bytes = (r.act->plane_elems() * sizeof(bf16) + 1023) & ~(size_t)1023;
+      items.push_back({bytes, r.t0, r.t1, 0, false});    // hi plane
+      items.push_back({bytes, r.t0, r.t1, 0, false});    // lo plane
+      arena_naive_bytes += 2 * bytes;
+    }
+    std::vector<int> order(items.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return items[a].bytes > items[b].bytes; });
+    size_t total = 0;
+    for (int idx : order) {
+      Item& it = items[idx];
+      std::vector<std::pair<size_t, size_t>> busy;       // [begin, end) of placed items alive at the same time
+      for (const Item& o : items)
+        if (o.placed && !(o.t1 < it.t0 || it.t1 < o.t0)) busy.push_back({o.off, o.off + o.bytes});
+      std::sort(busy.begin(), busy.end());
+      size_t off = 0;
+      for (auto& b : busy) {
+        if (off + it.bytes <= b.first) break;
+        off = std::max(off, b.second);
+      }
+      it.off = off; it.placed = true;
+      total = std::max(total, off + it.bytes);
+    }
+    uint8_t* base = (uint8_t*)mem.alloc(total);          // zero-filled
+    for (size_t i = 0; i < pending_acts.size(); ++i) {
+      pending_acts[i].act->hi = (bf16*)(base + items[2 * i].off);
+      pending_acts[i].act->lo = (bf16*)(base + items[2 * i + 1].off);
+    }
+    arena_bytes += total;
+    pending_acts.clear();
   }
 
   // ---------------------------------------------------------------------------------------
@@ -494,19 +548,25 @@ struct Engine {
         bd.f_c[i] = cout[i];
       }
     }
+    // schedule ticks (bdcn_forward): iteration i of the layer loop owns [10 i, 10 i + 9]; f[i] is written at 10 i (or
+    // during iteration i - 1 when it rides with the merged launch) and last read by iteration i + 1's convolution
     for (int i = 0; i < 13; ++i) {
       const int s = stage_of[i];
-      bd.f[i] = new_act(mem, mb, sh[s], sw_[s], cout[i] + ((i > 0 && bd.merged[i - 1]) ? 32 : 0));
+      bd.f[i] = new_act(mem, mb, sh[s], sw_[s], cout[i] + ((i > 0 && bd.merged[i - 1]) ? 32 : 0), 10 * (i - 1), 10 * (i + 1) + 9);
       debug_acts[std::string("features.") + names[i]] = {bd.f[i], {0, cout[i]}};
     }
     const int pc[4] = {64, 128, 256, 512};
-    for (int i = 0; i < 4; ++i) bd.pool[i] = new_act(mem, mb, sh[i + 1], sw_[i + 1], pc[i]);
+    static const int pool_src[4] = {1, 3, 6, 9};
+    for (int i = 0; i < 4; ++i)
+      bd.pool[i] = new_act(mem, mb, sh[i + 1], sw_[i + 1], pc[i], 10 * (pool_src[i] - 1), 10 * (pool_src[i] + 1) + 9);
+    static const int stage_first[5] = {0, 2, 4, 7, 10}, stage_last[5] = {1, 3, 6, 9, 12};
     for (int s = 0; s < 5; ++s) {
-      bd.o[s] = new_act(mem, mb, sh[s], sw_[s], 32);
+      bd.o[s] = new_act(mem, mb, sh[s], sw_[s], 32, 10 * stage_first[s], 10 * stage_last[s] + 9);
       bd.h[s] = sh[s]; bd.w[s] = sw_[s];
       bd.score[s] = (float*)mem.alloc((size_t)mb * sh[s] * sw_[s] * 2 * sizeof(float));
       debug_f32["score" + std::to_string(s + 1)] = {bd.score[s], {sh[s], sw_[s], 2}};
     }
+    commit_acts(mem);
     // conv1_1 on cat(img,img,img): sum the three input-channel slices (utils.py:649)
     {
       const HostTensor& w = sd_get(sd, "features.conv1_1.weight");
@@ -731,19 +791,26 @@ struct Engine {
     const int inter[5] = {32, 64, 96, 128, 128}, in_c[5] = {32, 38, 76, 115, 153}, op_c[5] = {38, 76, 115, 153, 153};
     const int bh[5] = {240, 120, 60, 30, 15}, bw[5] = {320, 160, 80, 40, 20};
     static const char* bname[5] = {"enc.down_block1", "enc.down_block2", "enc.down_block3", "enc.down_block4", "enc.bottleneck"};
-    es.h1 = new_act(mem, E, 240, 320, 32);
-    es.bt = new_act(mem, E, 15, 20, 160);
+    // schedule ticks (esf_forward): head 1000-1001; encoder block i owns [1010 + 10 i, +9] (instnorm_x, conv1, conv21,
+    // conv22, conv31, conv32, instnorm_td, TD.conv = +0 .. +7); up block j owns [1100 + 10 j, +9] (pre, conv11, conv12,
+    // conv21, conv22 = +0 .. +4); final 1140-1141; style encoder 1150-1159; regression head 1160-1163
+    auto TB = [](int i) { return 1010 + 10 * i; };
+    auto TD_ = [](int j) { return 1100 + 10 * j; };
+    es.h1 = new_act(mem, E, 240, 320, 32, 999, 1002);
+    es.bt = new_act(mem, E, 15, 20, 160, TB(4) + 6, 1170);
     debug_acts["bt"] = {es.bt, {0, 153}};
     for (int i = 0; i < 5; ++i) {
       Block& b = es.blk[i];
       b.in_c = in_c[i]; b.in_pad = round_up(in_c[i], 16); b.inter = inter[i]; b.op_c = op_c[i];
       b.H = bh[i]; b.W = bw[i];
       b.off_out = 0; b.off_x = inter[i]; b.off_x1 = b.off_x + b.in_pad; b.off_x22 = b.off_x1 + inter[i];
-      b.buf = new_act(mem, E, b.H, b.W, b.off_x22 + inter[i]);
-      b.xn = new_act(mem, E, b.H, b.W, b.in_pad);
-      b.t = new_act(mem, E, b.H, b.W, inter[i]);
+      // [out | x | x1 | x22]: x arrives with the previous block's TD.conv (head.conv2 for block 1); the skip [out, x] is
+      // last read by conv21 of up block 3 - i (the bottleneck's by its own TD)
+      b.buf = new_act(mem, E, b.H, b.W, b.off_x22 + inter[i], i == 0 ? 1000 : TB(i - 1) + 6, i < 4 ? TD_(3 - i) + 5 : TB(4) + 8);
+      b.xn = new_act(mem, E, b.H, b.W, b.in_pad, TB(i) - 1, TB(i) + 2);
+      b.t = new_act(mem, E, b.H, b.W, inter[i], TB(i) + 1, TB(i) + 6);
       const bool pool = i < 4;
-      b.tdin = new_act(mem, E, pool ? b.H / 2 : b.H, pool ? b.W / 2 : b.W, inter[i] + b.in_pad);
+      b.tdin = new_act(mem, E, pool ? b.H / 2 : b.H, pool ? b.W / 2 : b.W, inter[i] + b.in_pad, TB(i) + 5, TB(i) + 8);
       b.stats_C = inter[i] + b.in_pad;
       const std::string P = bname[i];
       debug_acts[P + ".x"] = {b.buf, {b.off_x, b.in_c}};
@@ -760,6 +827,37 @@ struct Engine {
       size_t off = 0;
       for (int i = 0; i < 5; ++i) { es.blk[i].stats = es.stats_all + off; off += (size_t)E * es.blk[i].stats_C * 2; }
     }
+    // ---- the remaining activations (decoder, final block, regression head, style encoder) are declared here too, so
+    // that the whole net is packed before any tensor map is encoded
+    const int d_in[4] = {cfg.add_edge ? 306 : 153, cfg.add_edge ? 180 : 115, cfg.add_edge ? 100 : 76, cfg.add_edge ? 62 : 38};
+    const int d_out[4] = {cfg.add_edge ? 180 : 115, cfg.add_edge ? 100 : 76, cfg.add_edge ? 62 : 38, 32};
+    for (int i = 0; i < 4; ++i) {
+      UpBlock& u = es.up[i];
+      Block& sk = es.blk[3 - i];
+      u.in_c = d_in[i]; u.out_c = d_out[i]; u.out_pad = round_up(d_out[i], 16);
+      u.skip_c = sk.inter + sk.in_c; u.H = sk.H; u.W = sk.W;
+      u.buf = new_act(mem, mb, u.H, u.W, u.out_pad, TD_(i) + 1, TD_(i) + 4);
+      u.t = new_act(mem, mb, u.H, u.W, u.out_pad, TD_(i), TD_(i) + 5);
+      u.out = new_act(mem, mb, u.H, u.W, u.out_pad, TD_(i) + 3, TD_(i) + 12);
+      u.y = new_act(mem, mb, u.H / 2, u.W / 2, 2 * u.out_pad, TD_(i) - 1, TD_(i) + 4);
+    }
+    es.fin = new_act(mem, mb, 240, 320, 32, 1139, 1142);
+    es.c1o = new_act(mem, mb, 15, 20, 128, 1159, 1164);
+    // hin: channels [153, 160) (and [313, 320)) are never written and must stay zero -> never shared
+    es.hin = cfg.add_seg ? new_act(mem, mb, 15, 20, cfg.add_edge ? 320 : 160) : nullptr;
+    int st_gh[5], st_gw[5], st_cin[5];
+    if (cfg.add_seg) {
+      const int sc[5] = {64, 128, 256, 256, 256};
+      int vh = 240, vw = 320;                      // valid region of the current layer's input
+      for (int i = 0; i < 5; ++i) {
+        if (i == 0) { st_gh[i] = vh + 6; st_gw[i] = vw; st_cin[i] = 32; }
+        else { st_gh[i] = (vh + 2) / 2; st_gw[i] = (vw + 2) / 2; st_cin[i] = 4 * sc[i - 1]; }
+        es.st_in[i] = new_act(mem, mb, st_gh[i], st_gw[i], st_cin[i], 1149, 1159);
+        es.st_out[i] = new_act(mem, mb, st_gh[i], st_gw[i], sc[i], 1149, 1159);
+        if (i > 0) { vh /= 2; vw /= 2; }
+      }
+    }
+    commit_acts(mem);
     // head: conv1 (SIMT first layer) -> h1; conv2 + lrelu + BN -> block1.x   (utils.py:1046-1050)
     {
       const HostTensor& w = sd_get(sd, "enc.head.conv1.weight");
@@ -824,8 +922,6 @@ struct Engine {
       finalize_conv(b.td);
     }
     // decoder
-    const int d_in[4] = {cfg.add_edge ? 306 : 153, cfg.add_edge ? 180 : 115, cfg.add_edge ? 100 : 76, cfg.add_edge ? 62 : 38};
-    const int d_out[4] = {cfg.add_edge ? 180 : 115, cfg.add_edge ? 100 : 76, cfg.add_edge ? 62 : 38, 32};
     static const char* uname[4] = {"dec.up_block4", "dec.up_block3", "dec.up_block2", "dec.up_block1"};
     // Each up block (RITnet_v2.py:79-88) applies two 1x1 convolutions to cat[upsample2x(x), skip(, x1)].
     // Both the bilinear interpolation and the 1x1 convolution are linear and the interpolation weights
@@ -835,12 +931,6 @@ struct Engine {
     for (int i = 0; i < 4; ++i) {
       UpBlock& u = es.up[i];
       Block& sk = es.blk[3 - i];
-      u.in_c = d_in[i]; u.out_c = d_out[i]; u.out_pad = round_up(d_out[i], 16);
-      u.skip_c = sk.inter + sk.in_c; u.H = sk.H; u.W = sk.W;
-      u.buf = new_act(mem, mb, u.H, u.W, u.out_pad);
-      u.t = new_act(mem, mb, u.H, u.W, u.out_pad);
-      u.out = new_act(mem, mb, u.H, u.W, u.out_pad);
-      u.y = new_act(mem, mb, u.H / 2, u.W / 2, 2 * u.out_pad);
       const std::string P = uname[i];
       debug_acts[P + ".out"] = {u.out, {0, u.out_c}};
       auto W = [&](const std::string& n) -> const HostTensor& { return sd_get(sd, P + "." + n + ".weight"); };
@@ -897,7 +987,6 @@ struct Engine {
       finalize_conv(u.c22);
     }
     // final convBlock: conv1 -> fin ; conv2 + lrelu + BN -> fp32 NCHW logits (both on the tensor cores)
-    es.fin = new_act(mem, mb, 240, 320, 32);
     debug_acts["dec.final.conv1"] = {es.fin, {0, 32}};
     {
       const HostTensor& w1 = sd_get(sd, "dec.final.conv1.weight");
@@ -928,8 +1017,6 @@ struct Engine {
     // whose outputs beyond the valid 14x18 region are never read; the rest of the head is one
     // fused SIMT kernel per frame (aux.cuh head_tail_kernel)
     EGN_CHECK(sd_get(sd, "elReg.c1.weight").shape[1] == Cf, "elReg.c1 input channels do not match the setting");
-    es.c1o = new_act(mem, mb, 15, 20, 128);
-    es.hin = cfg.add_seg ? new_act(mem, mb, 15, 20, cfg.add_edge ? 320 : 160) : nullptr;
     {
       std::vector<Piece> hp;
       if (cfg.add_seg) {
@@ -997,8 +1084,7 @@ struct Engine {
                   es.st_w[i][(((size_t)co * cin_t + par * cin_ref + c) * 2 + dy) * 2 + dx] = w.data[(((size_t)co * cin_ref + c) * 4 + r) * 4 + q];
                 }
         }
-        es.st_in[i] = new_act(mem, mb, gh, gw, cin_t);
-        es.st_out[i] = new_act(mem, mb, gh, gw, cout);
+        EGN_CHECK(gh == st_gh[i] && gw == st_gw[i] && cin_t == st_cin[i], Pn + ": staged shapes disagree with the declared ones");
         build_conv(es.st_conv[i], mem, Pn, {{es.st_in[i], 0, cin_t, 0}}, {{es.st_w[i].data(), bsv.data.data(), 1, 0}}, cout, cin_t,
                    kh, kw, gh, gw, mb);
         set_store_epilogue(es.st_conv[i], es.st_out[i], 0, ACT_RELU);

@@ -12,6 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 mode = sys.argv[1] if len(sys.argv) > 1 else "tc"
 cfg = sys.argv[2] if len(sys.argv) > 2 else "baseline_edge"
 os.environ["EGN_CONV"] = mode
+os.environ["EGN_NO_ARENA"] = "1"     # intermediate maps are read back after the forward: no buffer sharing
 
 import numpy as np
 import torch
