@@ -41,6 +41,7 @@ struct TcParams {
   int wide_b;                          // 1: hi*hi and hi*lo issue as ONE MMA of N = 2*n_tile against the stacked [W_hi; W_lo] tile (A_hi read once)
   int w_box;                           // 1: a W slot holds every tap of an activation box (one barrier round trip per box)
   int w_slot_taps;                     // taps per W slot (1 unless w_box)
+  int tap_triples;                     // 1: taps are ordered round-robin over three accumulator groups (phase-lattice MSBlock tail)
   int w_res;                           // 1: every (chunk, tap) weight tile of the layer stays resident in shared memory (loaded once per CTA)
   uint32_t a_plane_bytes, a_box_bytes, w_plane_bytes;
   int acc_bufs;                        // TMEM accumulator buffers (1 or 2)
@@ -233,13 +234,16 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // All MMAs of one (chunk, tap): NSUB sub-tiles x 2 K-steps x (1 or 3) split products, ordered so
-// that consecutive instructions target different accumulators.
+// that consecutive instructions target different accumulators.  Operands arrive as ready-made
+// descriptors: shared-memory addresses sit in the low 14 bits of a descriptor in 16-byte units, so the
+// caller forms a tap's descriptors by ADDING (offset >> 4) to the box / slot descriptor (one 64-bit add
+// each instead of rebuilding them) - with a single sub-tile per tile the issuing thread is otherwise
+// the bottleneck (~45 uniform instructions for 4 MMAs).
 template <int NSUB, int NPL, int WIDE>
-__device__ __forceinline__ void issue_tap(uint32_t sA, uint32_t a_plane, uint32_t sW, uint32_t w_plane,
+__device__ __forceinline__ void issue_tap(uint64_t dA_hi, uint32_t a_plane16, uint64_t dW_hi, uint32_t w_plane16,
                                           uint32_t d_tmem, uint32_t sub_cols, uint32_t idesc, uint32_t idesc_wide,
-                                          uint32_t first, uint32_t a_sbo, uint32_t a_sub16) {
-  const uint64_t dA_hi = make_desc(sA, a_sbo), dW_hi = make_desc(sW);
-  const uint64_t dA_lo = make_desc(sA + a_plane, a_sbo), dW_lo = make_desc(sW + w_plane);
+                                          uint32_t first, uint32_t a_sub16) {
+  const uint64_t dA_lo = dA_hi + a_plane16, dW_lo = dW_hi + w_plane16;
 #pragma unroll
   for (int k = 0; k < EGN_KC / 16; ++k) {
     const uint64_t koff = (uint64_t)((k * 32) >> 4);        // 16 bf16 = 32 bytes along K
@@ -265,6 +269,24 @@ __device__ __forceinline__ void issue_tap(uint32_t sA, uint32_t a_plane, uint32_
           mma_bf16(d_tmem + s * sub_cols, dA_hi + koff + (uint64_t)(s * a_sub16), dW_lo + koff, idesc, 1u);
       }
     }
+  }
+}
+
+// Three taps that feed three DIFFERENT accumulator groups (the phase-lattice MSBlock tail orders its taps
+// round-robin over the dilation groups), wide layout, one sub-tile: the MMAs of the three taps are
+// interleaved so that consecutive instructions never target the same TMEM columns.
+__device__ __forceinline__ void issue_triple_wide(const uint64_t (&dA)[3], uint32_t a_plane16, const uint64_t (&dW)[3],
+                                                  const uint32_t (&dcol)[3], uint32_t idesc, uint32_t idesc_wide,
+                                                  const uint32_t (&first)[3]) {
+#pragma unroll
+  for (int k = 0; k < EGN_KC / 16; ++k) {
+    const uint64_t koff = (uint64_t)((k * 32) >> 4);
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+      mma_bf16(dcol[g], dA[g] + koff, dW[g] + koff, idesc_wide, (k == 0) ? (first[g] ^ 1u) : 1u);
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+      mma_bf16(dcol[g], dA[g] + a_plane16 + koff, dW[g] + koff, idesc, 1u);
   }
 }
 
@@ -516,7 +538,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
       }
       if (ptm) {
-        long long* o = p.timing + (size_t)blockIdx.x * 12;
+        long long* o = p.timing + (size_t)blockIdx.x * 14;
         o[6] = ptm_a; o[7] = ptm_w; o[8] = clock64() - ptm_start;
       }
     }
@@ -536,7 +558,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t a_sbo = p.xshare ? (uint32_t)p.box_w * 64u : 512u;
       const uint32_t a_sub16 = (p.xshare ? (uint32_t)(p.sr * p.box_w) * 64u : 8192u) >> 4;
       const int nchunks = p.g.nchunks, ntaps = p.g.ntaps;
-      const uint32_t a_plane = p.a_plane_bytes, w_plane = p.w_plane_bytes;
+      const uint32_t a_plane16 = p.a_plane_bytes >> 4, w_plane16 = p.w_plane_bytes >> 4, w_tap16 = w_tap_bytes >> 4;
       const int dbg = p.dbg;
       int as = 0, ws = 0;
       uint32_t aph = 0, wph = 0;
@@ -548,10 +570,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         mbar_wait(w_full(0), 0u, p.err_flag, 5);
         fence_after();
       }
+      // the issuing warp only needs the tile's row index (the last tile row may hold fewer sub-tiles): it is advanced
+      // incrementally, the integer divisions of a full decode would sit on the critical path of every tile
+      const int row_len = p.n_blocks * p.tiles_x;                 // tiles per tile row
+      const int step_q = (int)gridDim.x / row_len, step_r = (int)gridDim.x % row_len, step_ty = step_q % p.tiles_y;
+      int dec_r = (int)blockIdx.x % row_len, ty = ((int)blockIdx.x / row_len) % p.tiles_y;
+      const int nsub_last = min(p.S, (p.g.H - (p.tiles_y - 1) * p.tr + p.sr - 1) / p.sr);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++use) {
         if (tm) tm_l = clock64();
-        const int ty = (tile / (p.n_blocks * p.tiles_x)) % p.tiles_y;
-        const int nsub = min(p.S, (p.g.H - ty * p.tr + p.sr - 1) / p.sr);
+        const int nsub = ty == p.tiles_y - 1 ? nsub_last : p.S;
+        {
+          dec_r += step_r;
+          int adv = step_ty;
+          if (dec_r >= row_len) { dec_r -= row_len; ++adv; }
+          ty += adv;
+          if (ty >= p.tiles_y) ty -= p.tiles_y;
+          if (ty >= p.tiles_y) ty -= p.tiles_y;
+        }
         const int ab = p.acc_bufs == 2 ? (use & 1) : 0;
         const uint32_t aphase = (p.acc_bufs == 2 ? (use >> 1) : use) & 1u;
         if (tm) { tm_c0 = clock64(); tm_h += tm_c0 - tm_l; }
@@ -573,16 +608,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 mbar_wait(a_full(as), aph, p.err_flag, 4);
                 if (tm) { const long long now = clock64(); tm_a += now - tm_c0; tm_c0 = now; }
                 fence_after();
-                const uint32_t sA = base + as * a_slot_bytes;
-                const uint32_t sW = w_base + (uint32_t)(c * ntaps + ld.tap0) * w_tap_bytes;
+                const uint64_t dA = make_desc(base + as * a_slot_bytes, a_sbo);
+                uint64_t dW = make_desc(w_base + (uint32_t)(c * ntaps + ld.tap0) * w_tap_bytes);
+                if (p.tap_triples && NSUB == 1 && WIDE) {
+                  // taps come in triples over the three accumulator groups: interleave their MMAs
+                  if (elect_one()) {
+                    if (!(dbg & 2)) {
+                      for (int j = 0; j < ld.ntaps; j += 3, dW += 3 * w_tap16) {
+                        const TcTapStep t0 = s_tap[ld.tap0 + j], t1 = s_tap[ld.tap0 + j + 1], t2 = s_tap[ld.tap0 + j + 2];
+                        const uint64_t tA[3] = {dA + (t0.a_off >> 4), dA + (t1.a_off >> 4), dA + (t2.a_off >> 4)};
+                        const uint64_t tW[3] = {dW, dW + w_tap16, dW + 2 * w_tap16};
+                        const uint32_t tD[3] = {d_base + t0.d_col, d_base + t1.d_col, d_base + t2.d_col};
+                        const uint32_t tF[3] = {(c == 0 && (t0.flags & 4u)) ? 1u : 0u, (c == 0 && (t1.flags & 4u)) ? 1u : 0u,
+                                                (c == 0 && (t2.flags & 4u)) ? 1u : 0u};
+                        issue_triple_wide(tA, a_plane16, tW, tD, idesc, idesc_wide, tF);
+                      }
+                    }
+                    if (tm) { const long long now = clock64(); tm_i += now - tm_c0; tm_c0 = now; }
+                    mma_commit(a_empty(as));
+                    if (tm) tm_k += clock64() - tm_c0;
+                  }
+                } else
                 if (elect_one()) {
                   if (!(dbg & 2)) {
                     TcTapStep nxt = s_tap[ld.tap0];
-                    for (int j = 0; j < ld.ntaps; ++j) {
+                    for (int j = 0; j < ld.ntaps; ++j, dW += w_tap16) {
                       const TcTapStep cur = nxt;
                       if (j + 1 < ld.ntaps) nxt = s_tap[ld.tap0 + j + 1];
                       const uint32_t first = (c == 0 && (cur.flags & 4u)) ? 1u : 0u;
-                      issue_tap<NSUB, NPL, WIDE>(sA + cur.a_off, a_plane, sW + j * w_tap_bytes, w_plane, d_base + cur.d_col, sub_cols, idesc, idesc_wide, first, a_sbo, a_sub16);
+                      issue_tap<NSUB, NPL, WIDE>(dA + (cur.a_off >> 4), a_plane16, dW, w_plane16, d_base + cur.d_col, sub_cols, idesc, idesc_wide, first, a_sub16);
                     }
                   }
                   if (tm) { const long long now = clock64(); tm_i += now - tm_c0; tm_c0 = now; }
@@ -604,7 +658,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 if (tm) tm_c0 = clock64();
                 mbar_wait(a_full(as), aph, p.err_flag, 4);
                 if (tm) tm_a += clock64() - tm_c0;
-                const uint32_t sA = base + as * a_slot_bytes;
+                const uint64_t dA = make_desc(base + as * a_slot_bytes, a_sbo);
                 for (int t0 = 0; t0 < ld.ntaps; t0 += p.w_slot_taps) {
                   const int nrun = min(p.w_slot_taps, ld.ntaps - t0);
                   const bool last_run = t0 + nrun >= ld.ntaps;
@@ -612,15 +666,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                   mbar_wait(w_full(ws), wph, p.err_flag, 5);
                   if (tm) { const long long now = clock64(); tm_w += now - tm_c0; tm_c0 = now; }
                   fence_after();
-                  const uint32_t sW = w_base + ws * w_slot_bytes;
+                  uint64_t dW = make_desc(w_base + ws * w_slot_bytes);
                   if (elect_one()) {
                     if (!(dbg & 2)) {
                       TcTapStep nxt = s_tap[ld.tap0 + t0];
-                      for (int j = 0; j < nrun; ++j) {
+                      for (int j = 0; j < nrun; ++j, dW += w_tap16) {
                         const TcTapStep cur = nxt;
                         if (j + 1 < nrun) nxt = s_tap[ld.tap0 + t0 + j + 1];
                         const uint32_t first = (c == 0 && (cur.flags & 4u)) ? 1u : 0u;
-                        issue_tap<NSUB, NPL, WIDE>(sA + cur.a_off, a_plane, sW + j * w_tap_bytes, w_plane, d_base + cur.d_col, sub_cols, idesc, idesc_wide, first, a_sbo, a_sub16);
+                        issue_tap<NSUB, NPL, WIDE>(dA + (cur.a_off >> 4), a_plane16, dW, w_plane16, d_base + cur.d_col, sub_cols, idesc, idesc_wide, first, a_sub16);
                       }
                     }
                     if (tm) { const long long now = clock64(); tm_i += now - tm_c0; tm_c0 = now; }
@@ -637,7 +691,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             return;
           }
           for (int c = 0; c < nchunks; ++c) {
-            uint32_t sA = 0;
+            uint64_t dA = 0;
             TcTapStep nxt = s_tap[0];
             for (int t = 0; t < ntaps; ++t) {
               const TcTapStep cur = nxt;
@@ -646,17 +700,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 if (tm) tm_c0 = clock64();
                 mbar_wait(a_full(as), aph, p.err_flag, 4);
                 if (tm) tm_a += clock64() - tm_c0;
-                sA = base + as * a_slot_bytes;
+                dA = make_desc(base + as * a_slot_bytes, a_sbo);
               }
               if (tm) tm_c0 = clock64();
               mbar_wait(w_full(ws), wph, p.err_flag, 5);
               if (tm) { const long long now = clock64(); tm_w += now - tm_c0; tm_c0 = now; }
               fence_after();
-              const uint32_t sW = w_base + ws * w_slot_bytes;
+              const uint64_t dW = make_desc(w_base + ws * w_slot_bytes);
               const uint32_t first = (c == 0 && (cur.flags & 4u)) ? 1u : 0u;
               if (elect_one()) {
                 if (!(dbg & 2))
-                  issue_tap<NSUB, NPL, WIDE>(sA + cur.a_off, a_plane, sW, w_plane, d_base + cur.d_col, sub_cols, idesc, idesc_wide, first, a_sbo, a_sub16);
+                  issue_tap<NSUB, NPL, WIDE>(dA + (cur.a_off >> 4), a_plane16, dW, w_plane16, d_base + cur.d_col, sub_cols, idesc, idesc_wide, first, a_sub16);
                 if (tm) { const long long now = clock64(); tm_i += now - tm_c0; tm_c0 = now; }
                 mma_commit(w_empty(ws));             // frees the weight slot when these MMAs retire
                 if (cur.flags & 2u) mma_commit(a_empty(as));   // last tap of this box
@@ -699,7 +753,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
       if (tm) {
         // counters are summed over lanes by the elected thread only for tm_i / tm_k
-        long long* o = p.timing + (size_t)blockIdx.x * 12;
+        long long* o = p.timing + (size_t)blockIdx.x * 14;
         if (lane == 0) { o[0] = clock64() - tm_start; o[1] = tm_te; o[2] = tm_a; o[3] = tm_w; o[5] = use; o[10] = tm_x; o[11] = tm_h; }
         if (tm_i) { o[4] = tm_i; o[9] = tm_k; }
       }
@@ -712,6 +766,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int mr = m >> p.bw_log2, mc = m & (bw - 1);
     int stat_flip = 0;
     int use = 0;
+    long long e_wait = 0, e_busy = 0;
     // upsample-add layers (decoder 1x1 convolutions): the (tr/2 + 2) x (bw/2 + 2) half-resolution pixels a tile
     // blends (indices clamped like F.interpolate, align_corners=False) x n_tile channels are staged in shared
     // memory one tile ahead: cp.async of the hi and lo 16-byte pieces (8 channels) side by side, which the SAME
@@ -820,7 +875,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           if (half == 0 && p.e.score_accum) sc_pre = reinterpret_cast<const float2*>(p.e.score)[pix];
         }
       }
+      long long et0 = 0;
+      if (p.timing) et0 = clock64();
       mbar_wait(tfull_bar(ab), aphase, p.err_flag, 6);
+      if (p.timing) { const long long now = clock64(); e_wait += now - et0; et0 = now; }
       fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * TC_ACC_STRIDE;
       if (UP) {
@@ -1053,6 +1111,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(ab));
+      if (p.timing) e_busy += clock64() - et0;
+    }
+    if (p.timing && warp == 2 && lane == 0) {
+      long long* o = p.timing + (size_t)blockIdx.x * 14;
+      o[12] = e_wait; o[13] = e_busy;
     }
   }
 
@@ -1195,9 +1258,15 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   }
   // narrow single-group layers are bound by the shared-memory read of the activation tile (an
   // M=128, N<=64 MMA takes (128+N)/4 cycles, tools/mma_probe.cu): fold hi*hi and hi*lo into one MMA
-  p.wide_b = (nsplit == 3 && g.groups == 1 && p.n_tile <= 64) ? 1 : 0;
+  static const int wide_max = getenv("EGN_TC_WIDE_MAX") ? atoi(getenv("EGN_TC_WIDE_MAX")) : 64;   // tuning knob
+  p.wide_b = (nsplit == 3 && g.groups == 1 && p.n_tile <= wide_max && 2 * p.n_tile <= 256) ? 1 : 0;
   if (const char* e = getenv("EGN_TC_WIDE")) p.wide_b = atoi(e) ? p.wide_b : 0;
   if (g.phase) { EGN_CHECK(nsplit == 3 && g.groups == 3 && p.n_tile == 32, "phase lattice is the MSBlock tail's layout"); p.wide_b = 1; }
+  p.tap_triples = 0;
+  if (g.phase && g.ntaps % 3 == 0 && !getenv("EGN_NO_TRIPLES")) {
+    p.tap_triples = 1;
+    for (int t = 0; t < g.ntaps; ++t) if (g.tap_grp[t] != t % 3) p.tap_triples = 0;
+  }
   const int cols = g.groups * p.n_tile * (p.wide_b ? 2 : 1);
   EGN_CHECK(cols <= 512, "accumulator groups exceed TMEM");
   // more sub-tiles per CTA tile amortise the weight stream and give the MMA pipe independent
@@ -1300,20 +1369,20 @@ static void tc_launch(const TcParams& p, int num_sms, cudaStream_t stream) {
   if (timing) {
     // debugging aid: per-role cycle counters of one launch, averaged over CTAs, to stderr
     static long long* buf = nullptr;
-    if (!buf) CUDA_OK(cudaMalloc(&buf, 148 * 12 * sizeof(long long)));
-    CUDA_OK(cudaMemsetAsync(buf, 0, 148 * 12 * sizeof(long long), stream));
+    if (!buf) CUDA_OK(cudaMalloc(&buf, 148 * 14 * sizeof(long long)));
+    CUDA_OK(cudaMemsetAsync(buf, 0, 148 * 14 * sizeof(long long), stream));
     TcParams q = p;
     q.timing = buf;
     if (q.e.up_hi) conv_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(q);
     else conv_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(q);
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(stream));
-    long long h[148 * 12];
+    long long h[148 * 14];
     CUDA_OK(cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost));
-    double a[12] = {0};
-    for (int b = 0; b < grid; ++b) for (int k = 0; k < 12; ++k) a[k] += (double)h[b * 12 + k] / grid;
-    fprintf(stderr, "tc_timing H=%d W=%d chunks=%d taps=%d ntile=%d S=%d na=%d nw=%d batch=%d | mma: total %.0f tempty %.0f a_full %.0f w_full %.0f issue %.0f commit %.0f tfullcommit %.0f head %.0f tiles %.1f | prod: a_empty %.0f w_empty %.0f total %.0f\n",
-            p.g.H, p.g.W, p.g.nchunks, p.g.ntaps, p.n_tile, p.S, p.na, p.nw, p.g.batch, a[0], a[1], a[2], a[3], a[4], a[9], a[10], a[11], a[5], a[6], a[7], a[8]);
+    double a[14] = {0};
+    for (int b = 0; b < grid; ++b) for (int k = 0; k < 14; ++k) a[k] += (double)h[b * 14 + k] / grid;
+    fprintf(stderr, "tc_timing H=%d W=%d chunks=%d taps=%d ntile=%d S=%d na=%d nw=%d batch=%d | mma: total %.0f tempty %.0f a_full %.0f w_full %.0f issue %.0f commit %.0f tfullcommit %.0f head %.0f tiles %.1f | prod: a_empty %.0f w_empty %.0f total %.0f | epi(warp 2): wait %.0f busy %.0f\n",
+            p.g.H, p.g.W, p.g.nchunks, p.g.ntaps, p.n_tile, p.S, p.na, p.nw, p.g.batch, a[0], a[1], a[2], a[3], a[4], a[9], a[10], a[11], a[5], a[6], a[7], a[8], a[12], a[13]);
     return;
   }
   if (p.e.up_hi) conv_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(p);

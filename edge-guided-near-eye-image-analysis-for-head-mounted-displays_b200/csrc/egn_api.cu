@@ -140,6 +140,7 @@ int egn_info(egn_ctx* ctx, egn_info_t* out) {
   out->device = e.device; out->num_sms = e.num_sms; out->micro_batch = e.mb;
   out->products_per_mac = e.nsplit; out->tensor_core_path = e.use_tc ? 1 : 0;
   out->workspace_bytes = (long long)(e.mem_bdcn.total + e.mem_esf.total + e.mem_misc.total);
+  out->activation_bytes_unshared = (long long)e.arena_naive_bytes;
   API_END
 }
 

@@ -275,7 +275,7 @@ struct Engine {
 
   void build_conv(ConvLayer& L, DevMem& mem, const std::string& name, const std::vector<Piece>& pieces,
                   const std::vector<PackSpec>& specs, int cout, int cin, int kh, int kw, int H, int W,
-                  int batch) {
+                  int batch, bool round_robin_groups = false) {
     L.name = name;
     L.cout = cout;
     ConvGeom& g = L.g;
@@ -334,6 +334,15 @@ struct Engine {
         for (int s = 0; s < kw; ++s)
           taps.push_back({gi, r, s, r * specs[gi].dil - specs[gi].pad, s * specs[gi].dil - specs[gi].pad});
     std::stable_sort(taps.begin(), taps.end(), [](const TapRef& a, const TapRef& b) { return a.dx < b.dx; });
+    if (round_robin_groups) {
+      // (phase-lattice MSBlock tail: one shared box serves every tap, so the order is free) group 0's k-th tap, group 1's
+      // k-th tap, group 2's k-th tap, ...: consecutive taps accumulate into different TMEM columns
+      std::vector<std::vector<TapRef>> per(g.groups);
+      for (const TapRef& t : taps) per[t.gi].push_back(t);
+      taps.clear();
+      for (int k = 0; k < kh * kw; ++k)
+        for (int gi = 0; gi < g.groups; ++gi) taps.push_back(per[gi][k]);
+    }
     for (int t = 0; t < g.ntaps; ++t) {
       g.tap_dy[t] = (int8_t)taps[t].dy;
       g.tap_dx[t] = (int8_t)taps[t].dx;
@@ -664,7 +673,9 @@ struct Engine {
           const HostTensor& bdv = sd_get(sd, mp + ".conv" + std::to_string(d) + ".bias");
           specs.push_back({wd.data.data(), bdv.data.data(), 4 * d, 4 * d});
         }
-        build_conv(Lt, mem, mp + ".tail", {{o_buf, o_off, 32, 0}}, specs, 32, 32, 3, 3, sh[s], sw_[s], mb);
+        static const int tail_phase = getenv("EGN_TAIL_PHASE") ? atoi(getenv("EGN_TAIL_PHASE")) : 4;
+        const int ph = (use_tc && nsplit == 3 && s <= 1 && tail_phase > 1) ? tail_phase : 0;
+        build_conv(Lt, mem, mp + ".tail", {{o_buf, o_off, 32, 0}}, specs, 32, 32, 3, 3, sh[s], sw_[s], mb, ph != 0);
         // collapsed conv{s}_{j}_down -> score_dsn{s}, score_dsn{s}_1 (both linear)
         const HostTensor& wd = sd_get(sd, "conv" + S + "_" + J + "_down.weight");   // [21][32]
         const HostTensor& bdn = sd_get(sd, "conv" + S + "_" + J + "_down.bias");
@@ -688,8 +699,7 @@ struct Engine {
         Lt.flops += 2.0 * 32 * 21 * sh[s] * sw_[s];      // conv_down (the reference's 1x1)
         // stages 1-2 (240x320, 120x160): run on the 4x4 polyphase lattice, where the three dilations are 1/2/3, one
         // shared activation box serves all 27 taps and the weights stay resident (conv_tc.cuh)
-        static const int tail_phase = getenv("EGN_TAIL_PHASE") ? atoi(getenv("EGN_TAIL_PHASE")) : 4;
-        Lt.phase = (use_tc && nsplit == 3 && s <= 1 && tail_phase > 1) ? tail_phase : 0;
+        Lt.phase = ph;
         finalize_conv(Lt);
       }
       bd.tail.cA[s] = (float)cA; bd.tail.cB[s] = (float)cB;

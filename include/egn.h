@@ -126,6 +126,7 @@ typedef struct egn_info_t {
   int products_per_mac;      /* bf16 tensor-core products per algorithmic MAC: 3 = hi*hi + lo*hi + hi*lo (default), 1 = plain bf16 */
   int tensor_core_path;      /* 1 = tcgen05 kernel, 0 = SIMT companion (EGN_CONV=simt, debugging only) */
   long long workspace_bytes; /* device memory held by the context so far */
+  long long activation_bytes_unshared; /* what the activation planes would take without liveness sharing (engine.cuh commit_acts) */
 } egn_info_t;
 int egn_info(egn_ctx* ctx, egn_info_t* out);
 

@@ -561,6 +561,48 @@ def test_engine_info_reports_the_precision_policy(env):
     assert info["workspace_bytes"] > 0 and info["num_sms"] >= 100
 
 
+def test_merged_launches_phase_lattice_tails_and_fused_pools(env):
+    """Round-2 restructurings of the BDCN graph, each against the SIMT companion on the same buffers:
+    msblock.conv riding with the VGG convolution that reads the same map (bdcn_new.py:120-160 / vgg16_c.py:65-88),
+    the stage-1/2 MSBlock tails on the 4x4 polyphase lattice (bdcn_new.py:49-55), and pools 1-3 written by the
+    producing epilogue (vgg16_c.py:15,20,27; the pooled maps feed conv2_1 / conv3_1 / conv4_1, so test_bdcn_edge_parity
+    pins them end to end - here the launch list shows that pools 1-3 no longer run as kernels)."""
+    em, dev = env["edge_model"], env["dev"]
+    ctx = em.context(dev)
+    em.edge(env["img"].to(dev))
+    for layer in ["features.conv2_2", "msblock2_1.conv", "features.conv3_3", "msblock3_2.conv", "msblock1_1.tail",
+                  "msblock1_2.tail", "msblock2_1.tail", "msblock2_2.tail"]:
+        d, r = ctx.conv_selfcheck(layer, 2)
+        assert d <= 1e-4 * max(r, 1.0), (layer, d, r)
+    # no standalone launch is left for the merged blocks
+    table = None
+    ctx.profile(True)
+    em.edge(env["img"].to(dev))
+    torch.cuda.synchronize()
+    table = ctx.profile_table()
+    ctx.profile(False)
+    names = [ln.split(",")[1] for ln in table.splitlines()[1:] if ln.startswith("conv,")]
+    assert "features.conv1_2+msblock1_1.conv" in names and "msblock1_1.conv" not in names and "msblock2_1.conv" not in names
+    assert not any(ln.startswith("aux,bdcn.maxpool") and int(ln.split(",")[9]) > 1 for ln in table.splitlines()), table
+
+
+def test_workspace_is_liveness_shared(env):
+    """One arena per net with interval packing (engine.cuh commit_acts): repeated forwards stay bit-identical
+    although buffers share memory, and the footprint is well below one allocation per activation."""
+    m, st, esd = _model(env, "baseline_edge")
+    dev = env["dev"]
+    x, e = env["img"].to(dev), env["edge_ref"].to(dev)
+    with torch.no_grad():
+        a = m(x, e, None, None, None, None, None, torch.zeros(2, 4, device=dev), 0, 0)
+        b = m(x, e, None, None, None, None, None, torch.zeros(2, 4, device=dev), 0, 0)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[4], b[4])
+    info = m.context(dev).info()
+    assert info["activation_bytes_unshared"] > 0
+    assert info["workspace_bytes"] < 0.75 * info["activation_bytes_unshared"], info
+    binfo = env["edge_model"].context(dev).info()
+    assert binfo["workspace_bytes"] < 0.75 * binfo["activation_bytes_unshared"], binfo
+
+
 def test_api_leaves_the_callers_device_alone(env):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
