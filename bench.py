@@ -155,6 +155,8 @@ def planted_parity(config, pos, argmax, el_pred, el_out):
 
 
 def dtype_label(info):
+    if info.get("lowered_layers"):
+        return "bf16x3 with %d layers lowered to two products (EGN_PRODUCTS probe: NOT the parity engine)" % info["lowered_layers"]
     if not info["tensor_core_path"]:
         return "f32-simt (EGN_CONV=simt debugging path: NOT the benchmarked engine)"
     if info["products_per_mac"] == 3:
@@ -469,7 +471,7 @@ def main():
         info = mctx.info()
         einfo = ectx.info()
     if (info["products_per_mac"] != 3 or not info["tensor_core_path"] or einfo["products_per_mac"] != 3
-            or not einfo["tensor_core_path"]) and not args.allow_nonparity:
+            or not einfo["tensor_core_path"] or info["lowered_layers"] or einfo["lowered_layers"]) and not args.allow_nonparity:
         raise SystemExit("bench.py: the engine runs with EGN_NSPLIT=%d / tensor_core_path=%d, which is not the parity "
                          "configuration; pass --allow-nonparity to time it anyway (the line is labelled)"
                          % (info["products_per_mac"], info["tensor_core_path"]))
@@ -486,7 +488,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": dtype_label(info), "data": "synthetic",
+                "vs_baseline": None, "dtype": dtype_label(dict(info, lowered_layers=info["lowered_layers"] + einfo["lowered_layers"])), "data": "synthetic",
                 "config": workload_config(args.config, B, world, args.micro_batch),
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(x_host.numel() * 4),
                         "d2h_bytes_per_step": int(out_am.numel() + 4 * (out_el.numel() + out_eo.numel() + out_lat.numel())),

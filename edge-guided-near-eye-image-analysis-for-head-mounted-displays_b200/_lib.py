@@ -10,7 +10,8 @@ LIB_PATH = os.path.join(_HERE, "libegn.so")
 class EgnInfo(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int), ("num_sms", ctypes.c_int), ("micro_batch", ctypes.c_int),
                 ("products_per_mac", ctypes.c_int), ("tensor_core_path", ctypes.c_int),
-                ("workspace_bytes", ctypes.c_longlong), ("activation_bytes_unshared", ctypes.c_longlong)]
+                ("workspace_bytes", ctypes.c_longlong), ("activation_bytes_unshared", ctypes.c_longlong),
+                ("lowered_layers", ctypes.c_int)]
 
 
 class EgnConfig(ctypes.Structure):

@@ -15,6 +15,7 @@ struct SimtParams {
   ConvGeom g;
   ConvEpi e;
   int nsplit;
+  int prod_mode;   // same meaning as TcParams::prod_mode
 };
 
 #define ST_PX 64
@@ -82,7 +83,8 @@ __global__ void __launch_bounds__(ST_THREADS) conv_simt_kernel(const SimtParams 
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float wh = sW[cog * 8 + i][k];
-          cur[i] = fmaf(a, wh, fmaf(al, wh, fmaf(a, sWl[cog * 8 + i][k], cur[i])));
+          const float lh = p.prod_mode == 1 ? 0.f : al, hl = p.prod_mode == 2 ? 0.f : sWl[cog * 8 + i][k];
+          cur[i] = fmaf(a, wh, fmaf(lh, wh, fmaf(a, hl, cur[i])));
         }
       }
     }

@@ -41,6 +41,7 @@ struct TcParams {
   int wide_b;                          // 1: hi*hi and hi*lo issue as ONE MMA of N = 2*n_tile against the stacked [W_hi; W_lo] tile (A_hi read once)
   int w_box;                           // 1: a W slot holds every tap of an activation box (one barrier round trip per box)
   int w_slot_taps;                     // taps per W slot (1 unless w_box)
+  int prod_mode;                       // precision probe (EGN_PRODUCTS): 0 = hi*hi + lo*hi + hi*lo, 1 = drop lo*hi (activations act as bf16), 2 = drop hi*lo (weights act as bf16)
   int tap_triples;                     // 1: taps are ordered round-robin over three accumulator groups (phase-lattice MSBlock tail)
   int w_res;                           // 1: every (chunk, tap) weight tile of the layer stays resident in shared memory (loaded once per CTA)
   uint32_t a_plane_bytes, a_box_bytes, w_plane_bytes;
@@ -242,7 +243,7 @@ __device__ __forceinline__ bool elect_one() {
 template <int NSUB, int NPL, int WIDE>
 __device__ __forceinline__ void issue_tap(uint64_t dA_hi, uint32_t a_plane16, uint64_t dW_hi, uint32_t w_plane16,
                                           uint32_t d_tmem, uint32_t sub_cols, uint32_t idesc, uint32_t idesc_wide,
-                                          uint32_t first, uint32_t a_sub16) {
+                                          uint32_t first, uint32_t a_sub16, int pm = 0) {
   const uint64_t dA_lo = dA_hi + a_plane16, dW_lo = dW_hi + w_plane16;
 #pragma unroll
   for (int k = 0; k < EGN_KC / 16; ++k) {
@@ -253,20 +254,26 @@ __device__ __forceinline__ void issue_tap(uint64_t dA_hi, uint32_t a_plane16, ui
 #pragma unroll
       for (int s = 0; s < NSUB; ++s)
         mma_bf16(d_tmem + s * sub_cols, dA_hi + koff + (uint64_t)(s * a_sub16), dW_hi + koff, idesc_wide, acc);
+      if (pm != 1) {
 #pragma unroll
-      for (int s = 0; s < NSUB; ++s)
-        mma_bf16(d_tmem + s * sub_cols, dA_lo + koff + (uint64_t)(s * a_sub16), dW_hi + koff, idesc, 1u);
+        for (int s = 0; s < NSUB; ++s)
+          mma_bf16(d_tmem + s * sub_cols, dA_lo + koff + (uint64_t)(s * a_sub16), dW_hi + koff, idesc, 1u);
+      }
     } else {
 #pragma unroll
       for (int s = 0; s < NSUB; ++s)
         mma_bf16(d_tmem + s * sub_cols, dA_hi + koff + (uint64_t)(s * a_sub16), dW_hi + koff, idesc, acc);
       if (NPL == 2) {
+        if (pm != 1) {
 #pragma unroll
-        for (int s = 0; s < NSUB; ++s)
-          mma_bf16(d_tmem + s * sub_cols, dA_lo + koff + (uint64_t)(s * a_sub16), dW_hi + koff, idesc, 1u);
+          for (int s = 0; s < NSUB; ++s)
+            mma_bf16(d_tmem + s * sub_cols, dA_lo + koff + (uint64_t)(s * a_sub16), dW_hi + koff, idesc, 1u);
+        }
+        if (pm != 2) {
 #pragma unroll
-        for (int s = 0; s < NSUB; ++s)
-          mma_bf16(d_tmem + s * sub_cols, dA_hi + koff + (uint64_t)(s * a_sub16), dW_lo + koff, idesc, 1u);
+          for (int s = 0; s < NSUB; ++s)
+            mma_bf16(d_tmem + s * sub_cols, dA_hi + koff + (uint64_t)(s * a_sub16), dW_lo + koff, idesc, 1u);
+        }
       }
     }
   }
@@ -559,7 +566,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t a_sub16 = (p.xshare ? (uint32_t)(p.sr * p.box_w) * 64u : 8192u) >> 4;
       const int nchunks = p.g.nchunks, ntaps = p.g.ntaps;
       const uint32_t a_plane16 = p.a_plane_bytes >> 4, w_plane16 = p.w_plane_bytes >> 4, w_tap16 = w_tap_bytes >> 4;
-      const int dbg = p.dbg;
+      const int dbg = p.dbg, pm = p.prod_mode;
       int as = 0, ws = 0;
       uint32_t aph = 0, wph = 0;
       int use = 0;                                   // tiles issued so far by this CTA
@@ -636,7 +643,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                       const TcTapStep cur = nxt;
                       if (j + 1 < ld.ntaps) nxt = s_tap[ld.tap0 + j + 1];
                       const uint32_t first = (c == 0 && (cur.flags & 4u)) ? 1u : 0u;
-                      issue_tap<NSUB, NPL, WIDE>(dA + (cur.a_off >> 4), a_plane16, dW, w_plane16, d_base + cur.d_col, sub_cols, idesc, idesc_wide, first, a_sub16);
+                      issue_tap<NSUB, NPL, WIDE>(dA + (cur.a_off >> 4), a_plane16, dW, w_plane16, d_base + cur.d_col, sub_cols, idesc, idesc_wide, first, a_sub16, pm);
                     }
                   }
                   if (tm) { const long long now = clock64(); tm_i += now - tm_c0; tm_c0 = now; }
@@ -674,7 +681,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         const TcTapStep cur = nxt;
                         if (j + 1 < nrun) nxt = s_tap[ld.tap0 + t0 + j + 1];
                         const uint32_t first = (c == 0 && (cur.flags & 4u)) ? 1u : 0u;
-                        issue_tap<NSUB, NPL, WIDE>(dA + (cur.a_off >> 4), a_plane16, dW, w_plane16, d_base + cur.d_col, sub_cols, idesc, idesc_wide, first, a_sub16);
+                        issue_tap<NSUB, NPL, WIDE>(dA + (cur.a_off >> 4), a_plane16, dW, w_plane16, d_base + cur.d_col, sub_cols, idesc, idesc_wide, first, a_sub16, pm);
                       }
                     }
                     if (tm) { const long long now = clock64(); tm_i += now - tm_c0; tm_c0 = now; }
@@ -710,7 +717,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               const uint32_t first = (c == 0 && (cur.flags & 4u)) ? 1u : 0u;
               if (elect_one()) {
                 if (!(dbg & 2))
-                  issue_tap<NSUB, NPL, WIDE>(dA + (cur.a_off >> 4), a_plane16, dW, w_plane16, d_base + cur.d_col, sub_cols, idesc, idesc_wide, first, a_sub16);
+                  issue_tap<NSUB, NPL, WIDE>(dA + (cur.a_off >> 4), a_plane16, dW, w_plane16, d_base + cur.d_col, sub_cols, idesc, idesc_wide, first, a_sub16, pm);
                 if (tm) { const long long now = clock64(); tm_i += now - tm_c0; tm_c0 = now; }
                 mma_commit(w_empty(ws));             // frees the weight slot when these MMAs retire
                 if (cur.flags & 2u) mma_commit(a_empty(as));   // last tap of this box
@@ -1261,9 +1268,10 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   static const int wide_max = getenv("EGN_TC_WIDE_MAX") ? atoi(getenv("EGN_TC_WIDE_MAX")) : 64;   // tuning knob
   p.wide_b = (nsplit == 3 && g.groups == 1 && p.n_tile <= wide_max && 2 * p.n_tile <= 256) ? 1 : 0;
   if (const char* e = getenv("EGN_TC_WIDE")) p.wide_b = atoi(e) ? p.wide_b : 0;
+  if (p.prod_mode == 2) p.wide_b = 0;            // the wide MMA cannot leave out hi*lo
   if (g.phase) { EGN_CHECK(nsplit == 3 && g.groups == 3 && p.n_tile == 32, "phase lattice is the MSBlock tail's layout"); p.wide_b = 1; }
   p.tap_triples = 0;
-  if (g.phase && g.ntaps % 3 == 0 && !getenv("EGN_NO_TRIPLES")) {
+  if (g.phase && g.ntaps % 3 == 0 && !getenv("EGN_NO_TRIPLES") && p.prod_mode == 0) {
     p.tap_triples = 1;
     for (int t = 0; t < g.ntaps; ++t) if (g.tap_grp[t] != t % 3) p.tap_triples = 0;
   }

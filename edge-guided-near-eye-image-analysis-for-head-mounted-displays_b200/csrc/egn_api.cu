@@ -141,6 +141,8 @@ int egn_info(egn_ctx* ctx, egn_info_t* out) {
   out->products_per_mac = e.nsplit; out->tensor_core_path = e.use_tc ? 1 : 0;
   out->workspace_bytes = (long long)(e.mem_bdcn.total + e.mem_esf.total + e.mem_misc.total);
   out->activation_bytes_unshared = (long long)e.arena_naive_bytes;
+  out->lowered_layers = 0;
+  for (auto& kv : e.conv_index) out->lowered_layers += kv.second->prod_mode != 0;
   API_END
 }
 

@@ -112,6 +112,7 @@ struct ConvLayer {
   int cout = 0;
   TcParams tc{};
   SimtParams simt{};
+  int prod_mode = 0;     // precision probe: products left out for this layer (TcParams::prod_mode)
   int phase = 0;         // tensor-core path runs on the phase x phase polyphase lattice of its input (MSBlock tails, stages 1-2)
   double flops = 0;      // algorithmic 2*MAC at unpadded sizes, per frame
   double prof_ms = 0;    // accumulated kernel time (profiling mode)
@@ -397,8 +398,30 @@ struct Engine {
     L.e.stats = stats; L.e.stats_C = stats_C; L.e.stats_coff = stats_coff;
   }
 
+  // EGN_PRODUCTS="prefix=mode,prefix=mode,...": layers whose name starts with `prefix` run with mode 1 (hi*hi + hi*lo:
+  // activations act as bf16) or 2 (hi*hi + lo*hi: weights act as bf16).  Precision probe only (tools/gpu_precision_probe.py);
+  // egn_info reports how many layers are lowered and bench.py refuses to time such a context as the parity engine.
+  static int product_policy(const std::string& name) {
+    const char* e = getenv("EGN_PRODUCTS");
+    if (!e) return 0;
+    std::string s(e);
+    size_t pos = 0;
+    while (pos < s.size()) {
+      size_t end = s.find(',', pos);
+      if (end == std::string::npos) end = s.size();
+      const std::string item = s.substr(pos, end - pos);
+      const size_t eq = item.find('=');
+      if (eq != std::string::npos && name.compare(0, eq, item, 0, eq) == 0) return atoi(item.c_str() + eq + 1);
+      pos = end + 1;
+    }
+    return 0;
+  }
+
   void finalize_conv(ConvLayer& L) {
     conv_index[L.name] = &L;
+    L.prod_mode = nsplit == 3 ? product_policy(L.name) : 0;
+    EGN_CHECK(!(L.phase && L.prod_mode == 2), L.name + ": the phase-lattice tail is wide-only (EGN_PRODUCTS mode 2 unsupported there)");
+    L.simt.prod_mode = L.prod_mode; L.tc.prod_mode = L.prod_mode;
     // SIMT companion
     L.simt.g = L.g; L.simt.e = L.e; L.simt.nsplit = nsplit;
     L.simt.w_hi = L.w_hi; L.simt.w_lo = L.w_lo;
