@@ -219,6 +219,72 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const NormApplyPara
 
 
 // ------------------------------------------------------------------------------------------
+// InstanceNorm folded into the 3x3 convolution that follows it (RITnet_v2.py:59-60: conv1(norm(x))):
+//   conv(W, (x - m) * r) = conv(W * r, x) - sum_{taps inside the frame} sum_k W[tap][:, k] * r[k] * m[k]
+// (zero padding applies to the NORMALISED map, so taps that fall outside the frame contribute nothing - the
+// mean term therefore depends on the pixel's border class: {first, inner, last} row x {first, inner, last} column).
+// One block per frame writes that frame's scaled split-bf16 weights and its 9 bias vectors; the convolution then
+// reads the raw map and the normalisation pass (one read + one write of the whole map) disappears.
+struct InFoldParams {
+  const float* w32;     // [ntaps][cout_pad][kpad] fp32, packed like the layer's bf16 weights (zero rows / columns for padding)
+  const float* bias;    // [cout_pad]
+  const double* sums;   // InstanceNorm statistics [N][sums_C][2]; K index k sits at channel sums_coff + k
+  int sums_C, sums_coff;
+  int ntaps, cout_pad, kpad, kreal, H, W;
+  int8_t tap_dy[9], tap_dx[9];
+  bf16* w_hi;           // [N][ntaps][cout_pad][kpad]
+  bf16* w_lo;
+  float* bias_fc;       // [N][9][cout_pad]
+};
+
+__global__ void __launch_bounds__(256) in_fold_kernel(const InFoldParams p) {
+  extern __shared__ float inf_sm[];
+  float* rstd = inf_sm;                 // [kpad]
+  float* mr = rstd + p.kpad;            // [kpad] mean * rstd
+  float* S = mr + p.kpad;               // [ntaps][cout_pad]
+  const int n = blockIdx.x;
+  const double inv = 1.0 / ((double)p.H * p.W);
+  for (int k = threadIdx.x; k < p.kpad; k += blockDim.x) {
+    float r = 0.f, m = 0.f;
+    if (k < p.kreal) {
+      const double s = p.sums[((size_t)n * p.sums_C + p.sums_coff + k) * 2];
+      const double q = p.sums[((size_t)n * p.sums_C + p.sums_coff + k) * 2 + 1];
+      const double mean = s * inv;
+      double var = q * inv - mean * mean;
+      if (var < 0.0) var = 0.0;
+      r = (float)(1.0 / sqrt(var + 1e-5));
+      m = (float)mean;
+    }
+    rstd[k] = r; mr[k] = m * r;
+  }
+  __syncthreads();
+  const int rows = p.ntaps * p.cout_pad;
+  const size_t fbase = (size_t)n * rows * p.kpad;
+  for (int i = threadIdx.x; i < rows * p.kpad; i += blockDim.x) {
+    const int k = i % p.kpad;
+    bf16 h, l;
+    split_bf16(p.w32[i] * rstd[k], h, l);
+    p.w_hi[fbase + i] = h; p.w_lo[fbase + i] = l;
+  }
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < p.kreal; ++k) s = fmaf(p.w32[(size_t)r * p.kpad + k], mr[k], s);
+    S[r] = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * p.cout_pad; i += blockDim.x) {
+    const int co = i % p.cout_pad, cls = i / p.cout_pad;
+    const int ry = cls / 3, rx = cls % 3;
+    float b = p.bias[co];
+    for (int t = 0; t < p.ntaps; ++t) {
+      const bool out = (ry == 0 && p.tap_dy[t] < 0) || (ry == 2 && p.tap_dy[t] > 0) || (rx == 0 && p.tap_dx[t] < 0) || (rx == 2 && p.tap_dx[t] > 0);
+      if (!out) b -= S[t * p.cout_pad + co];
+    }
+    p.bias_fc[((size_t)n * 9 + cls) * p.cout_pad + co] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Spatial mean of a channel window -> fp32 [B][Cs]  (latent, RITnet_v2.py:282).
 // Block per frame; blockDim.x = 4 * 160: four pixel quarters per channel, combined in shared memory.
 __global__ void spatial_mean_kernel(View src, float* out, int B, int HW, int Cs) {

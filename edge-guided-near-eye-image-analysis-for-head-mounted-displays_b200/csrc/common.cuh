@@ -121,6 +121,7 @@ struct ConvEpi {
   int mode, act;
   int cout_store;          // channels written (multiple of 8, <= cout_pad)
   const float* bias;       // [groups][cout_pad]
+  const float* bias_fc;    // optional per-frame, per-border-class bias [N][9][cout_pad] (InstanceNorm folded into the layer; tensor-core kernel only)
   const float* post_scale; // optional affine after the activation (eval BatchNorm), [cout_pad]
   const float* post_shift;
   bf16* out_hi;

@@ -41,6 +41,7 @@ struct TcParams {
   int wide_b;                          // 1: hi*hi and hi*lo issue as ONE MMA of N = 2*n_tile against the stacked [W_hi; W_lo] tile (A_hi read once)
   int w_box;                           // 1: a W slot holds every tap of an activation box (one barrier round trip per box)
   int w_slot_taps;                     // taps per W slot (1 unless w_box)
+  int w_frames;                        // > 0: PER-FRAME weights [frame][tap][cout_pad][kpad] (InstanceNorm folded into the layer, engine.cuh); w_map is 3-D
   int prod_mode;                       // precision probe (EGN_PRODUCTS): 0 = hi*hi + lo*hi + hi*lo, 1 = drop lo*hi (activations act as bf16), 2 = drop hi*lo (weights act as bf16)
   int tap_triples;                     // 1: taps are ordered round-robin over three accumulator groups (phase-lattice MSBlock tail)
   int w_res;                           // 1: every (chunk, tap) weight tile of the layer stays resident in shared memory (loaded once per CTA)
@@ -140,6 +141,14 @@ __device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint32_t bar
       "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 
@@ -518,8 +527,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                   mbar_expect_tx(w_full(ws), w_tx * nrun);
                   for (int j = 0; j < nrun; ++j) {
                     const int wrow = (ld.tap0 + t0 + j) * cout_pad + wrow0;
-                    tma_load_2d(&p.w_map[0], w_full(ws), sW + j * w_tap_bytes, c * EGN_KC, wrow);
-                    if (nplanes == 2) tma_load_2d(&p.w_map[1], w_full(ws), sW + j * w_tap_bytes + w_plane, c * EGN_KC, wrow);
+                    if (p.w_frames) {
+                      tma_load_3d(&p.w_map[0], w_full(ws), sW + j * w_tap_bytes, c * EGN_KC, wrow, n);
+                      if (nplanes == 2) tma_load_3d(&p.w_map[1], w_full(ws), sW + j * w_tap_bytes + w_plane, c * EGN_KC, wrow, n);
+                    } else {
+                      tma_load_2d(&p.w_map[0], w_full(ws), sW + j * w_tap_bytes, c * EGN_KC, wrow);
+                      if (nplanes == 2) tma_load_2d(&p.w_map[1], w_full(ws), sW + j * w_tap_bytes + w_plane, c * EGN_KC, wrow);
+                    }
                   }
                 }
                 if (++ws == nw) { ws = 0; wph ^= 1u; }
@@ -535,8 +549,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                   mbar_arrive(w_full(ws));
                 } else {
                   mbar_expect_tx(w_full(ws), w_tx);
-                  tma_load_2d(&p.w_map[0], w_full(ws), sW, c * EGN_KC, wrow);
-                  if (nplanes == 2) tma_load_2d(&p.w_map[1], w_full(ws), sW + w_plane, c * EGN_KC, wrow);
+                  if (p.w_frames) {
+                    tma_load_3d(&p.w_map[0], w_full(ws), sW, c * EGN_KC, wrow, n);
+                    if (nplanes == 2) tma_load_3d(&p.w_map[1], w_full(ws), sW + w_plane, c * EGN_KC, wrow, n);
+                  } else {
+                    tma_load_2d(&p.w_map[0], w_full(ws), sW, c * EGN_KC, wrow);
+                    if (nplanes == 2) tma_load_2d(&p.w_map[1], w_full(ws), sW + w_plane, c * EGN_KC, wrow);
+                  }
                 }
                 if (++ws == nw) { ws = 0; wph ^= 1u; }
               }
@@ -938,6 +957,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const bool valid = (py < p.g.H) && (px < p.g.W);
                 const size_t pix = ((size_t)n * p.g.H + py) * p.g.W + px;
                 float v[16];
+                if (!UP && p.e.bias_fc) {
+                  // InstanceNorm folded into this layer: the mean term is a bias that depends on which taps fall
+                  // inside the frame, i.e. on the pixel's border class (3 x 3 classes), per frame
+                  const int cls = (py == 0 ? 0 : (py >= p.g.H - 1 ? 2 : 1)) * 3 + (px == 0 ? 0 : (px >= p.g.W - 1 ? 2 : 1));
+                  const float4* bp = reinterpret_cast<const float4*>(p.e.bias_fc + ((size_t)n * 9 + cls) * p.g.cout_pad + cb);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float4 b4 = __ldg(bp + i);
+                    bias[4 * i] = b4.x; bias[4 * i + 1] = b4.y; bias[4 * i + 2] = b4.z; bias[4 * i + 3] = b4.w;
+                  }
+                }
                 if (UP) {
                   // + bilinear x2 upsample of the half-resolution tensor (same arithmetic as common.cuh upsample_add)
                   // from the staged patch: for o = 2i the taps are (i-1, i) with weights (0.25, 0.75), for o = 2i+1
@@ -1210,6 +1240,18 @@ static void make_w_map(CUtensorMap* map, const bf16* ptr, int rows, int kpad, in
   EGN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
 }
 
+// 3-D map over per-frame packed weights [frame][rows = ntaps*cout_pad][kpad], box (32, n_tile, 1).
+static void make_w_map_frames(CUtensorMap* map, const bf16* ptr, int frames, int rows, int kpad, int n_tile) {
+  cuuint64_t dims[3] = {(cuuint64_t)kpad, (cuuint64_t)rows, (cuuint64_t)frames};
+  cuuint64_t strides[2] = {(cuuint64_t)kpad * 2, (cuuint64_t)rows * kpad * 2};
+  cuuint32_t box[3] = {EGN_KC, (cuuint32_t)n_tile, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)ptr, dims, strides,
+                               box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EGN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(per-frame weights) failed: " + std::to_string((int)r));
+}
+
 static size_t tc_smem_bytes(const TcParams& p) {
   const int nplanes = p.nsplit == 1 ? 1 : 2;
   return 1024 + (size_t)p.na * nplanes * p.a_plane_bytes + (size_t)p.nw * p.w_slot_taps * nplanes * p.w_plane_bytes +
@@ -1350,7 +1392,7 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   p.w_res = 0;
   {
     const size_t all_w = w_slot * (size_t)g.ntaps * g.nchunks;
-    if (p.n_blocks == 1 && (all_w <= 48 * 1024 || g.phase) && budget >= 2 * a_slot + all_w && !getenv("EGN_TC_NO_WRES")) {
+    if (p.n_blocks == 1 && !p.w_frames && (all_w <= 48 * 1024 || g.phase) && budget >= 2 * a_slot + all_w && !getenv("EGN_TC_NO_WRES")) {
       p.w_res = 1; p.w_box = 1; p.w_slot_taps = g.ntaps * g.nchunks;
     }
   }

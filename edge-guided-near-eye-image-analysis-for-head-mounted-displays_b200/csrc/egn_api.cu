@@ -142,7 +142,7 @@ int egn_info(egn_ctx* ctx, egn_info_t* out) {
   out->workspace_bytes = (long long)(e.mem_bdcn.total + e.mem_esf.total + e.mem_misc.total);
   out->activation_bytes_unshared = (long long)e.arena_naive_bytes;
   out->lowered_layers = 0;
-  for (auto& kv : e.conv_index) out->lowered_layers += kv.second->prod_mode != 0;
+  for (auto& kv : e.conv_index) out->lowered_layers += (kv.second->prod_mode != 0) + (kv.second->w_frames != 0);
   API_END
 }
 
@@ -352,6 +352,8 @@ int egn_conv_selfcheck(egn_ctx* ctx, const char* layer, int frames, double* max_
     EGN_CHECK(it != e.conv_alias.end(), std::string("unknown conv layer: ") + layer);
   }
   ConvLayer& L = *it->second;
+  EGN_CHECK(!L.w_frames, std::string(layer) + ": InstanceNorm is folded into this layer (per-frame weights); the SIMT companion has no such mode - "
+                                              "set EGN_IN_FOLD=0 to cross-check it");
   const int n = std::min(frames, L.g.batch);
   const size_t px = (size_t)n * L.g.H * L.g.W;
   std::vector<float> a, b;

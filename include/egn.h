@@ -127,7 +127,8 @@ typedef struct egn_info_t {
   int tensor_core_path;      /* 1 = tcgen05 kernel, 0 = SIMT companion (EGN_CONV=simt, debugging only) */
   long long workspace_bytes; /* device memory held by the context so far */
   long long activation_bytes_unshared; /* what the activation planes would take without liveness sharing (engine.cuh commit_acts) */
-  int lowered_layers;        /* convolution layers that run with FEWER products than products_per_mac (EGN_PRODUCTS probe knob; 0 in the parity configuration) */
+  int lowered_layers;        /* convolution layers that run below the parity precision: fewer products than products_per_mac (EGN_PRODUCTS probe
+                              * knob) or InstanceNorm folded into per-frame weights (EGN_IN_FOLD experiment); 0 in the parity configuration */
 } egn_info_t;
 int egn_info(egn_ctx* ctx, egn_info_t* out);
 
