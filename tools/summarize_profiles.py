@@ -18,10 +18,16 @@ P = os.path.join(ROOT, "profiles")
 BDCN_ORDER = []
 _v = ["conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", "conv3_3", "conv4_1", "conv4_2", "conv4_3", "conv5_1", "conv5_2", "conv5_3"]
 _m = ["1_1", "1_2", "2_1", "2_2", "3_1", "3_2", "3_3", "4_1", "4_2", "4_3", "5_1", "5_2", "5_3"]
+_merged = {0, 2, 4, 5} if R >= "r02" else set()      # round 2: msblock i's conv rides with features.conv(i+1) (engine.cuh build_bdcn)
 for i in range(13):
-    if i > 0:
+    if i > 0 and (i - 1) not in _merged:
         BDCN_ORDER.append("features." + _v[i])
-    BDCN_ORDER += ["msblock%s.conv" % _m[i], "msblock%s.tail" % _m[i]]
+    if i in _merged:
+        BDCN_ORDER.append("features.%s+msblock%s.conv" % (_v[i + 1], _m[i]))
+    else:
+        BDCN_ORDER.append("msblock%s.conv" % _m[i])
+    BDCN_ORDER.append("msblock%s.tail" % _m[i])
+FRAMES = int(os.environ.get("PROFILE_FRAMES", "16"))
 ESF_ORDER = ["enc.head.conv2"]
 for b in ["down_block1", "down_block2", "down_block3", "down_block4", "bottleneck"]:
     ESF_ORDER += ["enc.%s.%s" % (b, c) for c in ["conv1", "conv21", "conv22", "conv31", "conv32", "TD.conv"]]
@@ -83,19 +89,20 @@ def conv_dram():
         for k, (lid, m) in enumerate(sorted(per.items())):
             name = order[k] if k < len(order) else "?"
             res.append((net, name, m.get("dram__bytes_read.sum", 0), m.get("dram__bytes_write.sum", 0), m.get("gpu__time_duration.sum", 0)))
-    out = ["# %s: DRAM traffic and duration of every conv_tc_kernel launch of one warm 16-frame pass (ESF encoder: 32 frames)" % R,
+    out = ["# %s: DRAM traffic and duration of every conv_tc_kernel launch of one warm %d-frame pass (ESF encoder: %d frames)" % (R, FRAMES, 2 * FRAMES),
            "net,layer,dram_read_MB,dram_write_MB,duration_us,dram_GBps"]
     tb = tt = 0
     for net, name, rd, wr, ns in res:
         out.append("%s,%s,%.2f,%.2f,%.1f,%.0f" % (net, name, rd / 1e6, wr / 1e6, ns / 1e3, (rd + wr) / max(ns, 1)))
         tb += rd + wr
         tt += ns
-    open(os.path.join(P, R + "_conv_dram.csv"), "w").write("\n".join(out) + "\n")
-    js = {"dram_bytes_per_launch": tb / len(res), "launches": len(res), "frames": 16,
-          "note": "mean dram__bytes_read.sum + dram__bytes_write.sum over the %d conv_tc_kernel launches of one warm 16-frame "
-                  "baseline_edge pass (ncu, profiles/%s_conv_dram.csv); scale by batch/16 for other micro-batches" % (len(res), R),
-          "total_dram_bytes_per_frame": tb / 16, "total_conv_us_per_frame_under_ncu": tt / 1e3 / 16}
-    json.dump(js, open(os.path.join(P, R + "_conv_traffic.json"), "w"), indent=1)
+    sfx = "" if FRAMES == 16 else "_b%d" % FRAMES
+    open(os.path.join(P, R + "_conv_dram%s.csv" % sfx), "w").write("\n".join(out) + "\n")
+    js = {"dram_bytes_per_launch": tb / len(res), "launches": len(res), "frames": FRAMES, "config": "baseline_edge",
+          "note": "mean dram__bytes_read.sum + dram__bytes_write.sum over the %d conv_tc_kernel launches of one warm %d-frame "
+                  "baseline_edge pass (ncu, profiles/%s_conv_dram%s.csv)" % (len(res), FRAMES, R, sfx),
+          "total_dram_bytes_per_frame": tb / FRAMES, "total_conv_us_per_frame_under_ncu": tt / 1e3 / FRAMES}
+    json.dump(js, open(os.path.join(P, R + "_conv_traffic%s.json" % sfx), "w"), indent=1)
     return js
 
 
@@ -129,8 +136,14 @@ def main():
     agg, tot = launches()
     js = conv_dram()
     caps = []
-    caps += full("conv_bdcn", ["msblock1_1.conv", "msblock1_1.tail", "features.conv1_2", "msblock1_2.conv", "msblock1_2.tail", "features.conv2_1"])
-    caps += full("conv_vgg3_2", ["features.conv3_2"])
+    if R >= "r02":
+        caps += full("conv_bdcn", ["features.conv1_2+msblock1_1.conv", "msblock1_1.tail (phase lattice)", "msblock1_2.conv", "msblock1_2.tail (phase lattice)",
+                                   "features.conv2_1", "features.conv2_2+msblock2_1.conv"])
+        caps += full("conv_vgg3_2", ["features.conv3_2+msblock3_1.conv"])
+        caps += full("conv_dec", ["dec.up_block1.pre", "dec.up_block1.conv11 (upsample-add)", "dec.up_block1.conv12", "dec.up_block1.conv21 (upsample-add)"])
+    else:
+        caps += full("conv_bdcn", ["msblock1_1.conv", "msblock1_1.tail", "features.conv1_2", "msblock1_2.conv", "msblock1_2.tail", "features.conv2_1"])
+        caps += full("conv_vgg3_2", ["features.conv3_2"])
     caps += full("conv_esf", ["enc.head.conv2", "enc.down_block1.conv1", "enc.down_block1.conv21", "enc.down_block1.conv22",
                               "enc.down_block1.conv31", "enc.down_block1.conv32", "enc.down_block1.TD.conv"])
     caps += full("aux_esf", [])
