@@ -33,6 +33,7 @@ struct FirstConvParams {
 
 #define FC_TW 32   // tile width (pixels)
 #define FC_TH 8    // tile height
+#define FC_YT 1    // vertically consecutive tiles per block (the weights are staged once per block)
 
 // Block = 8 x 32 output pixels.  The fp32 input window (10 x 34 per plane) and the weights are
 // staged in shared memory; a thread produces 8 output channels of 4 horizontally adjacent pixels,
@@ -42,12 +43,16 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p
   constexpr int G = COUT / 8;                 // 8-channel groups
   __shared__ __align__(16) float sw[CIN * 9 * COUT];           // [cin][tap][half][group][4]
   __shared__ float tile[CIN][FC_TH + 2][FC_TW + 2];
-  const int n = blockIdx.z, y0 = blockIdx.y * FC_TH, x0 = blockIdx.x * FC_TW;
+  const int n = blockIdx.z, x0 = blockIdx.x * FC_TW;
   for (int i = threadIdx.x; i < CIN * 9 * COUT; i += 256) {
     const int co = i % COUT, ct = i / COUT;                    // p.w is [cin][tap][cout]
     const int g = co >> 3, h = (co >> 2) & 1, k = co & 3;
     sw[((ct * 2 + h) * G + g) * 4 + k] = p.w[i];
   }
+  for (int yt = 0; yt < FC_YT; ++yt) {
+  const int y0 = (blockIdx.y * FC_YT + yt) * FC_TH;
+  if (y0 >= p.H) break;
+  if (yt) __syncthreads();                                     // everybody is done with the previous tile
 #pragma unroll
   for (int ci = 0; ci < CIN; ++ci) {
     const float* in = p.in[ci] + (size_t)n * p.fstride[ci];
@@ -104,6 +109,7 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const FirstConvParams p
         }
       }
     }
+  }
   }
 }
 
@@ -181,38 +187,57 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const NormApplyPara
   const int total = Ho * Wo * groups;
   const int per = (total + gridDim.x - 1) / gridDim.x;
   const int i0 = blockIdx.x * per, i1 = min(total, i0 + per);
+  if (!p.pool) {
+    // plain normalisation: four independent (pixel, 8-channel) items per thread and iteration, all eight 16-byte
+    // loads issued before the first use (one item per iteration left the kernel at 65 % of the HBM roofline)
+    const size_t fsrc = (size_t)(n + p.src.n_off) * p.H * p.W, fdst = (size_t)(n + p.dst.n_off) * Ho * Wo;
+    for (int base = i0 + threadIdx.x; base < i1; base += 4 * blockDim.x) {
+      BF8 h[4], l[4];
+      int gi[4], px[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = min(base + u * (int)blockDim.x, i1 - 1);
+        gi[u] = idx % groups; px[u] = idx / groups;
+        const size_t a = (fsrc + px[u]) * p.src.C + p.src.coff + gi[u] * 8;
+        h[u] = *reinterpret_cast<const BF8*>(p.src.hi + a);
+        l[u] = *reinterpret_cast<const BF8*>(p.src.lo + a);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (base + u * (int)blockDim.x >= i1) break;
+        float out[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 mr = na_mr[gi[u] * 8 + i];
+          out[i] = apply_act((join_bf16(h[u].v[i], l[u].v[i]) - mr.x) * mr.y, p.act);
+        }
+        store8(p.dst.hi, p.dst.lo, (fdst + px[u]) * p.dst.C + p.dst.coff + gi[u] * 8, out);
+      }
+    }
+    return;
+  }
   for (int idx = i0 + threadIdx.x; idx < i1; idx += blockDim.x) {
     const int gidx = idx % groups;
     const int pix = idx / groups;
     const int x = pix % Wo, y = pix / Wo;
     float out[8];
-    if (p.pool) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) out[i] = 0.f;
+    for (int i = 0; i < 8; ++i) out[i] = 0.f;
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
+    for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2) {
-          float v[8];
-          load8(p.src.hi, p.src.lo,
-                ((size_t)(n + p.src.n_off) * p.H * p.W + (size_t)(2 * y + r) * p.W + 2 * x + s2) * p.src.C + p.src.coff + gidx * 8, v);
+      for (int s2 = 0; s2 < 2; ++s2) {
+        float v[8];
+        load8(p.src.hi, p.src.lo,
+              ((size_t)(n + p.src.n_off) * p.H * p.W + (size_t)(2 * y + r) * p.W + 2 * x + s2) * p.src.C + p.src.coff + gidx * 8, v);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float2 mr = na_mr[gidx * 8 + i];
-            out[i] += apply_act((v[i] - mr.x) * mr.y, p.act);
-          }
+        for (int i = 0; i < 8; ++i) {
+          const float2 mr = na_mr[gidx * 8 + i];
+          out[i] += apply_act((v[i] - mr.x) * mr.y, p.act);
         }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) out[i] *= 0.25f;
-    } else {
-      float v[8];
-      load8(p.src.hi, p.src.lo, ((size_t)(n + p.src.n_off) * p.H * p.W + (size_t)y * p.W + x) * p.src.C + p.src.coff + gidx * 8, v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float2 mr = na_mr[gidx * 8 + i];
-        out[i] = apply_act((v[i] - mr.x) * mr.y, p.act);
       }
-    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] *= 0.25f;
     store8(p.dst.hi, p.dst.lo, ((size_t)(n + p.dst.n_off) * Ho * Wo + (size_t)y * Wo + x) * p.dst.C + p.dst.coff + gidx * 8, out);
   }
 }
@@ -314,6 +339,7 @@ struct BdcnTailParams {
   int h[5], w[5];
   const float* kern[5];    // [K][K] fp32 (kern[0] unused)
   int K[5], stride[5], crop[5];
+  int shift[5];            // log2(stride): the strides of bdcn_new.py:101-108 are 2 / 4 / 8 / 8
   float alpha[5], beta[5], cA[5], cB[5], fuse_bias;
   float* out;              // [N][H][W]
   // optional: the ten per-scale sigmoids BDCN.forward returns before the fused map (bdcn_new.py:163-191),
@@ -339,9 +365,10 @@ __global__ void bdcn_tail_kernel(const BdcnTailParams p) {
     const int st = p.stride[k], K = p.K[k];
     const int yy = y + p.crop[k], xx = x + p.crop[k];      // coordinate in the uncropped output
     // out[yy] = sum_i in[i] * kern[yy - i*st],  0 <= yy - i*st < K
-    int i0 = (yy - K + st) / st;  if (yy - K + 1 <= 0) i0 = 0;
-    int j0 = (xx - K + st) / st;  if (xx - K + 1 <= 0) j0 = 0;
-    const int i1 = min(yy / st, p.h[k] - 1), j1 = min(xx / st, p.w[k] - 1);
+    const int sh = p.shift[k];
+    int i0 = (yy - K + st) >> sh;  if (yy - K + 1 <= 0) i0 = 0;
+    int j0 = (xx - K + st) >> sh;  if (xx - K + 1 <= 0) j0 = 0;
+    const int i1 = min(yy >> sh, p.h[k] - 1), j1 = min(xx >> sh, p.w[k] - 1);
     float ua = 0.f, ub = 0.f;
     for (int i = i0; i <= i1; ++i) {
       const int ky = yy - i * st;

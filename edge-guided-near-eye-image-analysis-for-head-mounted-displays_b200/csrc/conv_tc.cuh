@@ -1216,14 +1216,16 @@ static void make_act_map(CUtensorMap* map, const bf16* ptr, int N, int H, int W,
 // address = n*H*W*C + yq*(d*W*C) + yp*(W*C) + xq*(d*C) + (xp*C + c): dims (d*C, W/d, H/d, d, N), box (32, bw, rows, 1, 1).
 // A box is then a dense window of ONE phase; out-of-bounds lattice coordinates zero-fill like the padding of the
 // dilated convolution.  Needs H % d == 0 and W % d == 0.
-static void make_act_map_phase(CUtensorMap* map, const bf16* ptr, int N, int H, int W, int C, int d, int box_w, int box_rows) {
+static void make_act_map_phase(CUtensorMap* map, const bf16* ptr, int N, int H, int W, int C, int d, int box_w, int box_rows,
+                               bool promo64 = false) {
   EGN_CHECK(H % d == 0 && W % d == 0, "phase lattice needs H and W divisible by the phase");
   cuuint64_t dims[5] = {(cuuint64_t)d * C, (cuuint64_t)(W / d), (cuuint64_t)(H / d), (cuuint64_t)d, (cuuint64_t)N};
   cuuint64_t strides[4] = {(cuuint64_t)d * C * 2, (cuuint64_t)d * W * C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
   cuuint32_t box[5] = {EGN_KC, (cuuint32_t)box_w, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)ptr, dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                               promo64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   EGN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(phase lattice) failed: " + std::to_string((int)r));
 }

@@ -453,8 +453,9 @@ struct Engine {
       for (int s = 0; s < L.nsrc; ++s) {
         const Act* a = L.src_act[s];
         if (L.phase) {
-          make_act_map_phase(&L.tc.a_map[0][s], a->hi, a->N, a->H, a->W, a->C, L.phase, L.tc.box_w, L.tc.box_rows);
-          make_act_map_phase(&L.tc.a_map[1][s], a->lo, a->N, a->H, a->W, a->C, L.phase, L.tc.box_w, L.tc.box_rows);
+          const bool p64 = a->C != 32;      // o as a 32-channel window of a wider [f | o] buffer: 64-byte promotion
+          make_act_map_phase(&L.tc.a_map[0][s], a->hi, a->N, a->H, a->W, a->C, L.phase, L.tc.box_w, L.tc.box_rows, p64);
+          make_act_map_phase(&L.tc.a_map[1][s], a->lo, a->N, a->H, a->W, a->C, L.phase, L.tc.box_w, L.tc.box_rows, p64);
           continue;
         }
         // channel window of this source the layer reads: [lo, hi) in 64-byte chunks
@@ -464,8 +465,12 @@ struct Engine {
         hi = std::min(hi, a->C);
         // (only where the operands stream from HBM: at 60x80 and below the buffers are L2-resident and
         //  the wider promotion is the faster one - measured on enc.down_block3.conv21/conv31)
+        // (a pixel of 96 or 160 channels is 192 / 320 bytes: 128-byte lines straddle pixels there, so a window that is
+        //  narrower than the pixel would drag the neighbouring channels in as well - measured on the merged [f | o]
+        //  buffers: msblock1_2.conv read 29.6 MB/frame for 19.7 MB of operands)
+        const bool partial = !(lo == 0 && hi == a->C);
         const bool promo64 = a->H * a->W >= 120 * 160 &&
-                             ((lo * 2) % 128 != 0 || ((hi * 2) % 128 != 0 && hi != a->C));
+                             ((lo * 2) % 128 != 0 || ((hi * 2) % 128 != 0 && hi != a->C) || (partial && (a->C * 2) % 128 != 0));
         make_act_map(&L.tc.a_map[0][s], a->hi, a->N, a->H, a->W, a->C, L.tc.box_w, L.tc.box_rows, promo64);
         make_act_map(&L.tc.a_map[1][s], a->lo, a->N, a->H, a->W, a->C, L.tc.box_w, L.tc.box_rows, promo64);
       }
@@ -748,12 +753,14 @@ struct Engine {
     }
     static const char* upn[5] = {"", "upsample_2", "upsample_4", "upsample_8", "upsample_8_5"};
     static const int upk[5] = {0, 4, 8, 16, 16}, ups[5] = {1, 2, 4, 8, 8}, upc[5] = {0, 1, 2, 4, 0};
-    bd.tail.kern[0] = nullptr; bd.tail.K[0] = 0; bd.tail.stride[0] = 1; bd.tail.crop[0] = 0;
+    bd.tail.kern[0] = nullptr; bd.tail.K[0] = 0; bd.tail.stride[0] = 1; bd.tail.crop[0] = 0; bd.tail.shift[0] = 0;
     for (int s = 1; s < 5; ++s) {
       const HostTensor& k = sd_get(sd, std::string(upn[s]) + ".weight");
       EGN_CHECK(k.numel() == upk[s] * upk[s], "upsample kernel size");
       bd.tail.kern[s] = mem.upload(k.data);
       bd.tail.K[s] = upk[s]; bd.tail.stride[s] = ups[s]; bd.tail.crop[s] = upc[s];
+      bd.tail.shift[s] = ups[s] == 2 ? 1 : ups[s] == 4 ? 2 : 3;
+      EGN_CHECK((1 << bd.tail.shift[s]) == ups[s], "upsampler strides are powers of two");
     }
     bd.tail.fuse_bias = fb.data[0];
     bd.tail.H = 240; bd.tail.W = 320;
@@ -1185,7 +1192,7 @@ struct Engine {
   }
 
   void launch_first(const FirstConvParams& fp, cudaStream_t st) {
-    const dim3 grid(ceil_div(fp.W, FC_TW), ceil_div(fp.H, FC_TH), fp.B);
+    const dim3 grid(ceil_div(fp.W, FC_TW), ceil_div(ceil_div(fp.H, FC_TH), FC_YT), fp.B);
     if (fp.cout == 64 && fp.cin == 1) first_conv_kernel<1, 64><<<grid, 256, 0, st>>>(fp);
     else if (fp.cout == 64 && fp.cin == 3) first_conv_kernel<3, 64><<<grid, 256, 0, st>>>(fp);
     else if (fp.cout == 32 && fp.cin == 1) first_conv_kernel<1, 32><<<grid, 256, 0, st>>>(fp);
