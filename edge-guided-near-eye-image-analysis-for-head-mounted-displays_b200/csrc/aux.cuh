@@ -187,57 +187,38 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const NormApplyPara
   const int total = Ho * Wo * groups;
   const int per = (total + gridDim.x - 1) / gridDim.x;
   const int i0 = blockIdx.x * per, i1 = min(total, i0 + per);
-  if (!p.pool) {
-    // plain normalisation: four independent (pixel, 8-channel) items per thread and iteration, all eight 16-byte
-    // loads issued before the first use (one item per iteration left the kernel at 65 % of the HBM roofline)
-    const size_t fsrc = (size_t)(n + p.src.n_off) * p.H * p.W, fdst = (size_t)(n + p.dst.n_off) * Ho * Wo;
-    for (int base = i0 + threadIdx.x; base < i1; base += 4 * blockDim.x) {
-      BF8 h[4], l[4];
-      int gi[4], px[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int idx = min(base + u * (int)blockDim.x, i1 - 1);
-        gi[u] = idx % groups; px[u] = idx / groups;
-        const size_t a = (fsrc + px[u]) * p.src.C + p.src.coff + gi[u] * 8;
-        h[u] = *reinterpret_cast<const BF8*>(p.src.hi + a);
-        l[u] = *reinterpret_cast<const BF8*>(p.src.lo + a);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (base + u * (int)blockDim.x >= i1) break;
-        float out[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float2 mr = na_mr[gi[u] * 8 + i];
-          out[i] = apply_act((join_bf16(h[u].v[i], l[u].v[i]) - mr.x) * mr.y, p.act);
-        }
-        store8(p.dst.hi, p.dst.lo, (fdst + px[u]) * p.dst.C + p.dst.coff + gi[u] * 8, out);
-      }
-    }
-    return;
-  }
   for (int idx = i0 + threadIdx.x; idx < i1; idx += blockDim.x) {
     const int gidx = idx % groups;
     const int pix = idx / groups;
     const int x = pix % Wo, y = pix / Wo;
     float out[8];
+    if (p.pool) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) out[i] = 0.f;
+      for (int i = 0; i < 8; ++i) out[i] = 0.f;
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
+      for (int r = 0; r < 2; ++r)
 #pragma unroll
-      for (int s2 = 0; s2 < 2; ++s2) {
-        float v[8];
-        load8(p.src.hi, p.src.lo,
-              ((size_t)(n + p.src.n_off) * p.H * p.W + (size_t)(2 * y + r) * p.W + 2 * x + s2) * p.src.C + p.src.coff + gidx * 8, v);
+        for (int s2 = 0; s2 < 2; ++s2) {
+          float v[8];
+          load8(p.src.hi, p.src.lo,
+                ((size_t)(n + p.src.n_off) * p.H * p.W + (size_t)(2 * y + r) * p.W + 2 * x + s2) * p.src.C + p.src.coff + gidx * 8, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float2 mr = na_mr[gidx * 8 + i];
-          out[i] += apply_act((v[i] - mr.x) * mr.y, p.act);
+          for (int i = 0; i < 8; ++i) {
+            const float2 mr = na_mr[gidx * 8 + i];
+            out[i] += apply_act((v[i] - mr.x) * mr.y, p.act);
+          }
         }
-      }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) out[i] *= 0.25f;
+      for (int i = 0; i < 8; ++i) out[i] *= 0.25f;
+    } else {
+      float v[8];
+      load8(p.src.hi, p.src.lo, ((size_t)(n + p.src.n_off) * p.H * p.W + (size_t)y * p.W + x) * p.src.C + p.src.coff + gidx * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 mr = na_mr[gidx * 8 + i];
+        out[i] = apply_act((v[i] - mr.x) * mr.y, p.act);
+      }
+    }
     store8(p.dst.hi, p.dst.lo, ((size_t)(n + p.dst.n_off) * Ho * Wo + (size_t)y * Wo + x) * p.dst.C + p.dst.coff + gidx * 8, out);
   }
 }
