@@ -1209,7 +1209,8 @@ struct Engine {
     ap.src = make_view(*src, coff); ap.dst = make_view(*dst, dcoff); ap.sums = stats; ap.sums_C = stats_C; ap.sums_coff = coff;
     ap.B = batch; ap.H = src->H; ap.W = src->W; ap.Cv = Cv; ap.act = act; ap.pool = pool ? 1 : 0;
     const long long per_frame = (long long)(pool ? src->H / 2 : src->H) * (pool ? src->W / 2 : src->W) * (Cv / 8);
-    dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(64, per_frame / 2048)), (unsigned)batch);
+    static const int max_blocks = getenv("EGN_IN_BLOCKS") ? atoi(getenv("EGN_IN_BLOCKS")) : 64;   // tuning knob: pixel slabs per frame
+    dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(max_blocks, per_frame / 2048)), (unsigned)batch);
     instnorm_apply_kernel<<<grid, 256, (size_t)Cv * sizeof(float2), st>>>(ap);
     CUDA_OK(cudaGetLastError());
     launches += 1;
