@@ -54,7 +54,8 @@ struct TcParams {
   // channels, both planes) is staged in shared memory by the epilogue warps with cp.async, one tile ahead
   int up_rows, up_cols;                // patch rows / columns (half-resolution pixels)
   uint32_t up_pix_stride, up_plane_stride, up_patch_bytes;
-  int dbg;                             // timing experiments only: 1 = skip epilogue body, 2 = skip MMAs, 4 = skip activation TMA loads, 8 = skip weight TMA loads
+  int dbg;                             // timing experiments only: 1 = skip epilogue body, 2 = skip MMAs, 4 = skip activation TMA loads, 8 = skip weight TMA loads,
+                                       // 32 = skip the epilogue's global stores, 64 = skip its TMEM reads
   int8_t aload_dx[TC_MAX_ALOADS];
   uint8_t aload_tap0[TC_MAX_ALOADS], aload_ntaps[TC_MAX_ALOADS];
   int* err_flag;
@@ -317,13 +318,16 @@ __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint
 }
 
 // 16 consecutive channels of one pixel to both planes as one 32-byte store each (full sectors).
+#ifndef ST16
+#define ST16 "st.global.v8.b32"
+#endif
 __device__ __forceinline__ void store16(bf16* hi, bf16* lo, size_t idx, const float v[16]) {
   uint32_t h[8], l[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) split_pack2(v[2 * i], v[2 * i + 1], h[i], l[i]);
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+  asm volatile(ST16 " [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"l"(hi + idx), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+  asm volatile(ST16 " [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"l"(lo + idx), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7]) : "memory");
 }
 
@@ -936,9 +940,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           for (int s0 = 0; s0 < nsub; s0 += 2) {
             uint32_t r[2][16];
             const uint32_t sstride = p.wide_b ? 2 * p.n_tile : p.n_tile;
+            if (p.dbg & 64) {                      // timing experiment: no TMEM reads
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { r[0][i] = 0; r[1][i] = 0; }
+            } else {
             tmem_ld16(tbase + s0 * sstride + c0, r[0]);
             if (s0 + 1 < nsub) tmem_ld16(tbase + (s0 + 1) * sstride + c0, r[1]);
-            if (p.wide_b) {                        // add the hi*lo partial sums held in columns [n, 2n)
+            }
+            if (p.wide_b && !(p.dbg & 64)) {       // add the hi*lo partial sums held in columns [n, 2n)
               uint32_t q[2][16];
               tmem_ld16(tbase + s0 * sstride + p.n_tile + c0, q[0]);
               if (s0 + 1 < nsub) tmem_ld16(tbase + (s0 + 1) * sstride + p.n_tile + c0, q[1]);
@@ -1013,7 +1022,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     for (int i = 0; i < 4; ++i)
                       if (i < p.e.logits_c) dst[(size_t)i * p.g.H * p.g.W] = v[i];
                   }
-                } else if (valid) store16(p.e.out_hi, p.e.out_lo, pix * p.e.out_C + p.e.out_coff + cb, v);
+                } else if (valid && !(p.dbg & 32)) store16(p.e.out_hi, p.e.out_lo, pix * p.e.out_C + p.e.out_coff + cb, v);
                 if (!UP && p.e.pool_hi && cb < p.e.pool_ch) {
                   // fused 2x2 / stride 2 max-pool: the window partners are lanes ^1 (x) and ^bw (y) of this warp (tile
                   // origins are even, H and W are even, so a window is entirely valid or entirely outside the frame);
@@ -1269,6 +1278,17 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   // wide layers run as 256-pixel x 128-channel CTA tiles (two sub-tiles, both TMEM buffers): the
   // weight stream per tile halves against 128 x 256 and a run of three taps fits one weight slot
   if (cout_pad >= 256 && cout_pad % 128 == 0 && !getenv("EGN_TC_N256")) p.n_blocks = cout_pad / 128;
+  // An MMA into the accumulator the PREVIOUS MMA wrote costs 1.5-1.7x (tools/mma_align_probe.cu: 61 / 77 / 109 cycles at
+  // N = 32 / 64 / 128 with one accumulator, 49 / 60 / 81 with two alternating, the 40 / 48 / 64-cycle bound from three
+  // on).  EXPERIMENT, off by default (EGN_TC_ACC3=1): layers with a lot of MMA work per tile (K chunks x taps >= 36)
+  // take THREE OR FOUR interleaved sub-tile accumulators in ONE TMEM buffer instead of one or two with a second
+  // buffer (288 = 256 + 32 merged channels split 3 x 96 for that).  Measured, same box: every affected layer got
+  // SLOWER (conv2_2+msblock 18.6 -> 20.0 us/frame, conv3_1 6.8 -> 7.8, conv3_x+msblock 15.3 -> 17.5, dec.up_block3
+  // 3.3 -> 3.7): the epilogue of a 384-512-pixel x 96-160-channel tile (TMEM reads at 64 B/cycle plus its stores)
+  // and the drain / refill around it cost more than the shorter MMAs save.
+  static const bool acc3 = getenv("EGN_TC_ACC3") && atoi(getenv("EGN_TC_ACC3")) != 0;
+  const bool heavy = acc3 && g.groups == 1 && !g.phase && g.nchunks * g.ntaps >= 36;
+  if (heavy && cout_pad == 288) p.n_blocks = 3;
   EGN_CHECK(cout_pad % (16 * p.n_blocks) == 0, "cout_pad must split into equal 16-aligned N tiles");
   p.n_tile = cout_pad / p.n_blocks;
   EGN_CHECK(p.n_tile % 16 == 0 && p.n_tile <= 256, "bad n_tile");
@@ -1329,6 +1349,12 @@ static void tc_configure(TcParams& p, int cout_pad, int nsplit) {
   if (rows_avail >= 2 && 2 * cols <= TC_ACC_STRIDE) p.S = 2;
   if (rows_avail >= 4 && 4 * cols <= TC_ACC_STRIDE) p.S = 4;
   if (getenv("EGN_TC_S4SINGLE") && p.wide_b && rows_avail >= 4 && 4 * cols <= 512) p.S = 4;           // tuning knob: one TMEM buffer
+  if (heavy && !p.wide_b && p.S < 3 && 3 * cols > TC_ACC_STRIDE) {
+    // one TMEM buffer, three or four accumulators (only where two buffers cannot hold three of them)
+    const int s1 = std::min(std::min(4, 512 / cols), rows_avail);
+    const int rows_last = rows_avail % s1;            // sub-tiles of the last (partial) tile row
+    if (s1 >= 3 && (rows_last == 0 || rows_last >= 3 || rows_avail / s1 >= 4)) p.S = s1;
+  }
   if (const char* e = getenv("EGN_TC_SMAX")) p.S = std::min(p.S, std::max(1, atoi(e)));   // tuning knob
   while (latency_mode && p.S > 1 && tiles_at(p.S, p.n_blocks) < sm_target) p.S /= 2;      // fewer sub-tiles, more CTAs
   p.tr = p.S * p.sr;
