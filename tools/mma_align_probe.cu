@@ -113,6 +113,12 @@ int main() {
   long long* d;
   cudaMalloc(&d, 8);
   printf("# cycles per MMA (M=128, K=16); pair = wide N=2n MMA followed by the N=n MMA of a narrow layer (cycles per PAIR)\n");
+  // the merged VGG + MSBlock layers: N = 160 (one 160-column accumulator per buffer today) and N = 144 / 96
+  for (int N : {160, 144, 96}) {
+    run<1>(d, N, 0, 0, 512, 160);
+    run<2>(d, N, 0, 0, 512, 160);
+    run<3>(d, N, 0, 0, 512, 160);
+  }
   for (int pair = 0; pair < 2; ++pair)
     for (int N : {32, 64, 128}) {
       if (pair && N == 128) continue;
