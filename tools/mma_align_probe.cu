@@ -46,8 +46,12 @@ __global__ void __launch_bounds__(128, 1) probe(int N, int pair, uint32_t a_shif
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tm = tmem_slot;
   if (warp == 0) {
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * N) >> 3) << 17) | ((128u >> 4) << 24);
+    // a_shift bit 0 set (never a real shift: shifts are multiples of 64): M = 64 instead of 128 (the transposed formulation
+    // of the MSBlock tail would stack 2 x 32 weight rows as the M operand)
+    const uint32_t M = (a_shift & 1u) ? 64u : 128u;
+    a_shift &= ~1u;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((M >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * N) >> 3) << 17) | ((M >> 4) << 24);
     uint32_t pred = 0;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     long long t0 = 0, t1 = 0;
@@ -105,7 +109,7 @@ static void run(long long* d, int N, int pair, uint32_t shift, uint32_t sbo, uin
   cudaError_t e = cudaDeviceSynchronize();
   long long h = 0;
   cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-  printf("%s N=%3d accumulators=%d (%3u columns apart, boundary ops %u) sbo=%4u a_shift=%3u : %6.1f cycles%s\n", pair ? "pair" : "one ", N, NACC, acc_stride & ~7u, acc_stride & 7u, sbo, shift,
+  printf("%s M=%3d N=%3d accumulators=%d (%3u columns apart, boundary ops %u) sbo=%4u a_shift=%3u : %6.1f cycles%s\n", pair ? "pair" : "one ", (shift & 1u) ? 64 : 128, N, NACC, acc_stride & ~7u, acc_stride & 7u, sbo, shift & ~1u,
          (double)h / ((double)(12 / NACC * NACC) * iters), e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
 
@@ -113,6 +117,11 @@ int main() {
   long long* d;
   cudaMalloc(&d, 8);
   printf("# cycles per MMA (M=128, K=16); pair = wide N=2n MMA followed by the N=n MMA of a narrow layer (cycles per PAIR)\n");
+  // M = 64 against M = 128 at N = 256 / 128 (three accumulators would need 768 columns at N = 256: two)
+  run<2>(d, 256, 0, 0, 512, 256);
+  run<2>(d, 256, 0, 1, 512, 256);
+  run<3>(d, 128, 0, 0, 512, 128);
+  run<3>(d, 128, 0, 1, 512, 128);
   // the merged VGG + MSBlock layers: N = 160 (one 160-column accumulator per buffer today) and N = 144 / 96
   for (int N : {160, 144, 96}) {
     run<1>(d, N, 0, 0, 512, 160);
