@@ -111,6 +111,7 @@ int egn_plan(egn_ctx* ctx, int micro_batch) {
   EGN_CHECK(micro_batch >= 1 && micro_batch <= 1024, "micro_batch must be in [1,1024]");
   EGN_CHECK(!ctx->eng.built_bdcn && !ctx->eng.built_esf, "plan must precede the first forward");
   ctx->eng.mb = micro_batch;
+  ctx->eng.decide_concurrency();
   API_END
 }
 

@@ -198,6 +198,43 @@ struct Engine {
 
   ~Engine() {
     mem_bdcn.release(); mem_esf.release(); mem_misc.release();
+    for (cudaEvent_t e : side_events) cudaEventDestroy(e);
+    if (side_stream) cudaStreamDestroy(side_stream);
+  }
+
+  // ---- side stream (streaming micro-batches only).  With a handful of frames most launches fill a fraction of the
+  // SMs, and the graph has independent branches: every MSBlock (its `conv` and its tail only feed the score maps,
+  // bdcn_new.py:120-160) next to the VGG trunk, and the regression head (utils.py:1013-1037, reads the bottleneck
+  // only) next to the decoder.  In that regime the branches run on an internal second stream, forked and joined
+  // with events relative to the caller's stream (legal inside a caller's graph capture too).  Buffers are then NOT
+  // shared by liveness (the schedule ticks no longer describe the execution order; the workspace is small there).
+  cudaStream_t side_stream = nullptr;
+  std::vector<cudaEvent_t> side_events;
+  size_t side_used = 0;
+  bool concurrent = false;            // decided by egn_plan: micro-batch <= EGN_SIDE_STREAM_MAX_MB (default 16)
+
+  void decide_concurrency() {
+    const int max_mb = getenv("EGN_SIDE_STREAM_MAX_MB") ? atoi(getenv("EGN_SIDE_STREAM_MAX_MB")) : 16;
+    concurrent = use_tc && mb <= max_mb;
+  }
+  cudaEvent_t next_event() {
+    if (side_used == side_events.size()) {
+      cudaEvent_t e;
+      CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      side_events.push_back(e);
+    }
+    return side_events[side_used++];
+  }
+  // work enqueued on `to` after this call waits for everything enqueued on `from` so far
+  void stream_edge(cudaStream_t from, cudaStream_t to) {
+    cudaEvent_t e = next_event();
+    CUDA_OK(cudaEventRecord(e, from));
+    CUDA_OK(cudaStreamWaitEvent(to, e, 0));
+  }
+  cudaStream_t side_of(cudaStream_t st) {
+    if (!concurrent || profiling) return st;
+    if (!side_stream) CUDA_OK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+    return side_stream;
   }
 
   // per-device function attributes (dynamic shared memory above 48 KB); called by egn_create with
@@ -224,7 +261,7 @@ struct Engine {
     std::unique_ptr<Act> a(new Act());
     a->N = N; a->H = H; a->W = W; a->C = C;
     static const bool no_arena = getenv("EGN_NO_ARENA") != nullptr;
-    if (no_arena) {
+    if (no_arena || concurrent) {
       const size_t bytes = a->plane_elems() * sizeof(bf16);
       a->hi = (bf16*)mem.alloc(bytes);
       a->lo = (bf16*)mem.alloc(bytes);
@@ -790,14 +827,20 @@ struct Engine {
       for (int c = 0; c < planes; ++c) { fp.in[c] = x + ((size_t)b0 * planes + c) * hw; fp.fstride[c] = (long long)planes * hw; }
       aux("bdcn.first_conv", st, [&] { launch_first(fp, st); });
       static const int pool_after[13] = {-1, 0, -1, 1, -1, -1, 2, -1, -1, 3, -1, -1, -1};
+      // the MSBlock branch (standalone `conv` launches and all tails, in block order: the tails of a stage accumulate
+      // into one score map) runs on the side stream when there is one; `ss == st` otherwise
+      const cudaStream_t ss = side_of(st);
+      side_used = 0;
       for (int i = 0; i < 13; ++i) {
         if (i > 0 && !bd.merged[i - 1]) run_conv(bd.vgg[i], nb, st);
         if (bd.merged[i]) run_conv(bd.vgg[i + 1], nb, st);       // features.conv(i+1) + msblock(i).conv in one launch
-        else run_conv(bd.ms_in[i], nb, st);
-        run_conv(bd.ms_tail[i], nb, st);
+        if (ss != st) stream_edge(st, ss);                       // f[i] (and a merged o) are complete
+        if (!bd.merged[i]) run_conv(bd.ms_in[i], nb, ss);
+        run_conv(bd.ms_tail[i], nb, ss);
         if (pool_after[i] >= 0 && !bd.pool_fused[pool_after[i]])
           aux("bdcn.maxpool", st, [&] { maxpool(bd.f[i], bd.pool[pool_after[i]], pool_after[i] == 3 ? 1 : 2, nb, st); });
       }
+      if (ss != st) stream_edge(ss, st);                         // the score maps are complete
       BdcnTailParams tp = bd.tail;
       tp.N = nb; tp.out = edge_out + b0 * hw;
       tp.side = side ? side + b0 * hw : nullptr; tp.side_stride = (long long)B * (long long)hw;
@@ -1266,6 +1309,24 @@ struct Engine {
       const int eoff = nb;
       spatial_mean_kernel<<<nb, 640, 0, st>>>(make_view(*es.bt, 0, 0), latent + (size_t)b0 * 153, nb, 300, 153);
       CUDA_OK(cudaGetLastError()); ++launches;
+      // ---- regression head (utils.py:1013-1037): reads the bottleneck only unless the AdaIN branch feeds it
+      auto run_head = [&](cudaStream_t hs) {
+        if (cfg.add_seg) {
+          AdainApplyParams ap;
+          ap.src[0] = make_view(*es.bt, 0, 0); ap.src[1] = make_view(*es.bt, 0, eoff);
+          ap.nsrc = cfg.add_edge ? 2 : 1; ap.Cs = 153; ap.Cslot = 160; ap.adain = es.adain;
+          ap.dst = make_view(*es.hin, 0); ap.B = nb; ap.HW = 300;
+          adain_apply_kernel<<<nb, 320, 0, hs>>>(ap); CUDA_OK(cudaGetLastError()); ++launches;
+        }
+        run_conv_impl(es.head_c1, nb, hs, cfg.add_seg ? -1 : eoff);
+        HeadTailParams h = es.head;
+        h.B = nb; h.el_out = el_out + (size_t)b0 * 10;
+        head_tail_kernel<<<nb, HEAD_TAIL_THREADS, HEAD_TAIL_SMEM, hs>>>(h); CUDA_OK(cudaGetLastError()); ++launches;
+      };
+      // streaming micro-batches: the head runs on the side stream next to the decoder
+      const cudaStream_t hs = cfg.add_seg ? st : side_of(st);
+      side_used = 0;
+      if (hs != st) { stream_edge(st, hs); run_head(hs); }
       // ---- decoder
       for (int i = 0; i < 4; ++i) {
         UpBlock& u = es.up[i];
@@ -1311,19 +1372,8 @@ struct Engine {
       }
       // ---- regression head
       if (profiling) { if (prof_used >= 8192) profile_resolve(); profile_begin(st); }
-      if (cfg.add_seg) {
-        AdainApplyParams ap;
-        ap.src[0] = make_view(*es.bt, 0, 0); ap.src[1] = make_view(*es.bt, 0, eoff);
-        ap.nsrc = cfg.add_edge ? 2 : 1; ap.Cs = 153; ap.Cslot = 160; ap.adain = es.adain;
-        ap.dst = make_view(*es.hin, 0); ap.B = nb; ap.HW = 300;
-        adain_apply_kernel<<<nb, 320, 0, st>>>(ap); CUDA_OK(cudaGetLastError()); ++launches;
-      }
-      run_conv_impl(es.head_c1, nb, st, cfg.add_seg ? -1 : eoff);
-      {
-        HeadTailParams h = es.head;
-        h.B = nb; h.el_out = el_out + (size_t)b0 * 10;
-        head_tail_kernel<<<nb, HEAD_TAIL_THREADS, HEAD_TAIL_SMEM, st>>>(h); CUDA_OK(cudaGetLastError()); ++launches;
-      }
+      if (hs == st) run_head(st);
+      else stream_edge(hs, st);
       if (profiling) profile_end(st, 0, nullptr, "esf.reg_head", 0);
     }
   }

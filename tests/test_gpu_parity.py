@@ -589,7 +589,9 @@ def test_merged_launches_phase_lattice_tails_and_fused_pools(env):
 def test_workspace_is_liveness_shared(env):
     """One arena per net with interval packing (engine.cuh commit_acts): repeated forwards stay bit-identical
     although buffers share memory, and the footprint is well below one allocation per activation."""
-    m, st, esd = _model(env, "baseline_edge")
+    # micro-batches above 16 frames share buffers by liveness (streaming micro-batches keep dedicated buffers: their
+    # independent branches run on a second stream, engine.cuh side_of)
+    m, st, esd = _model(env, "baseline_edge", mb=24)
     dev = env["dev"]
     x, e = env["img"].to(dev), env["edge_ref"].to(dev)
     with torch.no_grad():
@@ -599,8 +601,20 @@ def test_workspace_is_liveness_shared(env):
     info = m.context(dev).info()
     assert info["activation_bytes_unshared"] > 0
     assert info["workspace_bytes"] < 0.75 * info["activation_bytes_unshared"], info
-    binfo = env["edge_model"].context(dev).info()
+    em = env["egn"].BDCN(); em.load_state_dict(env["bsd"]); em = em.cuda().eval(); em.micro_batch = 24
+    e1, e2 = em.edge(x), em.edge(x)
+    assert torch.equal(e1, e2)
+    np.testing.assert_allclose(e1.cpu().numpy(), env["edge_ref"].numpy(), atol=5e-4)
+    binfo = em.context(dev).info()
     assert binfo["workspace_bytes"] < 0.75 * binfo["activation_bytes_unshared"], binfo
+    # the same frames through a streaming micro-batch (side-stream branches, dedicated buffers) give the same bits
+    m2, _, _ = _model(env, "baseline_edge", mb=2)
+    with torch.no_grad():
+        c = m2(x, e, None, None, None, None, None, torch.zeros(2, 4, device=dev), 0, 0)
+    assert m2.context(dev).info()["activation_bytes_unshared"] == 0
+    np.testing.assert_allclose(c[4].cpu().numpy(), a[4].cpu().numpy(), atol=2e-5)
+    egn = env["egn"]
+    assert (egn.get_predictions(c[0], m2) == egn.get_predictions(a[0], m)).float().mean().item() > 0.9999
 
 
 def test_api_leaves_the_callers_device_alone(env):
