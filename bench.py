@@ -382,6 +382,8 @@ def main():
     assert args.gpus == world, "--gpus must equal WORLD_SIZE (launch N>1 with torch.distributed.run)"
 
     st = synth.SETTINGS[args.config]
+    # the step drives both modules in stream order on one stream, so their activation arenas may be one pool
+    egn_b200.share_workspace(not os.environ.get("EGN_NO_SHARE_WORKSPACE"))
     edge_model = egn_b200.BDCN(); edge_model.load_state_dict(synth.make_bdcn_state(0))
     model = egn_b200.DenseNet2D(st); model.load_state_dict(synth.make_esf_state(st, 0))
     edge_model = edge_model.to(dev).eval(); model = model.to(dev).eval()
@@ -516,7 +518,8 @@ def main():
                 "hbm_used_gb": round((torch.cuda.mem_get_info(dev)[1] - torch.cuda.mem_get_info(dev)[0]) / 1e9, 1),
                 "metrics_check": acc.result()["frames"], "parity": parity,
                 "rank_ms_per_step": rank_ms,
-                "workspace_gb": round((info["workspace_bytes"] + einfo["workspace_bytes"]) / 1e9, 2)}
+                "workspace_gb": round((info["workspace_bytes"] + einfo["workspace_bytes"] + max(info["shared_pool_bytes"], einfo["shared_pool_bytes"])) / 1e9, 2),
+                "workspace_note": "one activation pool per device shared by the BDCN and ESF-Net contexts (egn_share_workspace: the evaluator runs them in stream order)"}
         if gf:
             line["roofline"]["whole_step_frac_of_policy_ceiling"] = fps / world * gf / 1000.0 / peak_tf * products
         if not args.no_cpu_baseline:

@@ -11,7 +11,7 @@ class EgnInfo(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int), ("num_sms", ctypes.c_int), ("micro_batch", ctypes.c_int),
                 ("products_per_mac", ctypes.c_int), ("tensor_core_path", ctypes.c_int),
                 ("workspace_bytes", ctypes.c_longlong), ("activation_bytes_unshared", ctypes.c_longlong),
-                ("lowered_layers", ctypes.c_int)]
+                ("shared_pool_bytes", ctypes.c_longlong), ("lowered_layers", ctypes.c_int)]
 
 
 class EgnConfig(ctypes.Structure):
@@ -22,7 +22,7 @@ class EgnConfig(ctypes.Structure):
 EXPORTS = ["egn_last_error", "egn_version", "egn_create", "egn_destroy", "egn_set_weights", "egn_plan",
            "egn_bdcn_forward", "egn_bdcn_forward_all", "egn_info", "egn_esf_forward", "egn_seg_post", "egn_metrics_accumulate",
            "egn_ellipse_refine", "egn_preprocess_u8", "egn_forward_loss", "egn_launch_count", "egn_flops_per_frame", "egn_debug_read",
-           "egn_conv_selfcheck", "egn_profile", "egn_profile_read", "egn_profile_table"]
+           "egn_conv_selfcheck", "egn_profile", "egn_profile_read", "egn_profile_table", "egn_share_workspace"]
 
 _lib = None
 
@@ -47,6 +47,7 @@ def load():
     lib.egn_destroy.argtypes = [vp]
     lib.egn_set_weights.argtypes = [vp, ci, vp, ctypes.c_size_t]
     lib.egn_plan.argtypes = [vp, ci]
+    lib.egn_share_workspace.argtypes = [ci]
     lib.egn_bdcn_forward.argtypes = [vp, vp, ci, vp, ci, vp]
     lib.egn_bdcn_forward_all.argtypes = [vp, vp, ci, vp, vp, ci, vp]
     lib.egn_info.argtypes = [vp, ctypes.POINTER(EgnInfo)]

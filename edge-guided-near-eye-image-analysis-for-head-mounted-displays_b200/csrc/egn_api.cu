@@ -105,6 +105,11 @@ int egn_set_weights(egn_ctx* ctx, int net, const void* blob, size_t bytes) {
   API_END
 }
 
+int egn_share_workspace(int enable) {
+  share_workspace_flag() = enable != 0;
+  return 0;
+}
+
 int egn_plan(egn_ctx* ctx, int micro_batch) {
   API_BEGIN
   EGN_CHECK(ctx, "null context");
@@ -142,6 +147,8 @@ int egn_info(egn_ctx* ctx, egn_info_t* out) {
   out->products_per_mac = e.nsplit; out->tensor_core_path = e.use_tc ? 1 : 0;
   out->workspace_bytes = (long long)(e.mem_bdcn.total + e.mem_esf.total + e.mem_misc.total);
   out->activation_bytes_unshared = (long long)e.arena_naive_bytes;
+  out->shared_pool_bytes = 0;
+  if (e.uses_pool) out->shared_pool_bytes = (long long)shared_pools()[e.device].bytes;
   out->lowered_layers = 0;
   for (auto& kv : e.conv_index) out->lowered_layers += (kv.second->prod_mode != 0) + (kv.second->w_frames != 0);
   API_END

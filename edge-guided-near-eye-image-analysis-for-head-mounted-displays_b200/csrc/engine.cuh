@@ -95,6 +95,17 @@ struct DevMem {
 
 static inline bf16 host_bf16(float v) { return __float2bfloat16_rn(v); }
 
+// Opt-in (egn_share_workspace / EGN_SHARE_WORKSPACE=1): ONE activation arena per device for every context of the
+// process.  The BDCN context's buffers are dead once its edge map is out, so an evaluator that drives both modules
+// in stream order (bench.py, calc_acc) can lend them to the ESF-Net: max(19, 37) instead of 19 + 37 GB at micro-batch
+// 256.  Off by default: two independent nn.Modules may legitimately run on different streams.
+struct SharedPool { void* base = nullptr; size_t bytes = 0; int refs = 0; };
+static std::map<int, SharedPool>& shared_pools() { static std::map<int, SharedPool> m; return m; }
+static bool& share_workspace_flag() {
+  static bool f = getenv("EGN_SHARE_WORKSPACE") && atoi(getenv("EGN_SHARE_WORKSPACE")) != 0;
+  return f;
+}
+
 struct Piece {       // a run of reference input channels living in a buffer
   const Act* buf;
   int buf_c, len, n_off;
@@ -196,8 +207,13 @@ struct Engine {
     size_t stats_bytes;
   } es;
 
+  bool uses_pool = false;
   ~Engine() {
     mem_bdcn.release(); mem_esf.release(); mem_misc.release();
+    if (uses_pool) {
+      SharedPool& p = shared_pools()[device];
+      if (--p.refs == 0) { cudaFree(p.base); p = SharedPool(); }
+    }
     for (cudaEvent_t e : side_events) cudaEventDestroy(e);
     if (side_stream) cudaStreamDestroy(side_stream);
   }
@@ -274,6 +290,22 @@ struct Engine {
 
   void commit_acts(DevMem& mem) {
     if (pending_acts.empty()) return;
+    const bool share = share_workspace_flag();
+    if (share) {
+      // buffers that rely on never-written channels staying zero cannot live in memory another context writes
+      std::vector<ActReq> rest;
+      for (auto& r : pending_acts) {
+        if (r.t1 == 0x7fffffff) {
+          const size_t bytes = r.act->plane_elems() * sizeof(bf16);
+          r.act->hi = (bf16*)mem.alloc(bytes); r.act->lo = (bf16*)mem.alloc(bytes);
+          arena_naive_bytes += 2 * bytes;
+        } else {
+          rest.push_back(r);
+        }
+      }
+      pending_acts.swap(rest);
+      if (pending_acts.empty()) return;
+    }
     struct Item { size_t bytes; int t0, t1; size_t off; bool placed; };
     std::vector<Item> items;
     for (auto& r : pending_acts) {
@@ -300,13 +332,28 @@ struct Engine {
       it.off = off; it.placed = true;
       total = std::max(total, off + it.bytes);
     }
-    uint8_t* base = (uint8_t*)mem.alloc(total);          // zero-filled
+    uint8_t* base = nullptr;
+    if (share) {
+      SharedPool& p = shared_pools()[device];
+      if (!p.base) {
+        // sized for the larger net of this micro-batch up front (the ESF-Net with the edge branch: ~145 MB per frame)
+        p.bytes = std::max(total, (size_t)mb * 150u * 1000u * 1000u);
+        CUDA_OK(cudaMalloc(&p.base, p.bytes));
+        CUDA_OK(cudaMemset(p.base, 0, p.bytes));
+      }
+      if (p.bytes >= total) {
+        base = (uint8_t*)p.base;
+        if (!uses_pool) { ++p.refs; uses_pool = true; }
+      }
+    }
+    if (!base) base = (uint8_t*)mem.alloc(total);        // zero-filled
     for (size_t i = 0; i < pending_acts.size(); ++i) {
       pending_acts[i].act->hi = (bf16*)(base + items[2 * i].off);
       pending_acts[i].act->lo = (bf16*)(base + items[2 * i + 1].off);
     }
     arena_bytes += total;
     pending_acts.clear();
+    (void)share;
   }
 
   // ---------------------------------------------------------------------------------------

@@ -48,6 +48,12 @@ int egn_destroy(egn_ctx* ctx);
  * tensors under their reference names (format: csrc/engine.cuh parse_blob). */
 int egn_set_weights(egn_ctx* ctx, int net, const void* blob, size_t bytes);
 
+/* Opt-in, process-wide, before the first forward of the contexts it should cover: every context of a device draws
+ * its activation arena from ONE pool.  Only for callers that run their contexts in stream order on one stream (an
+ * evaluator that owns both modules: bench.py, calc_acc) - the BDCN context's buffers are dead once its edge map is
+ * out, so the ESF-Net may overwrite them.  Off by default (independent modules may run on different streams). */
+int egn_share_workspace(int enable);
+
 /* Sizes the workspace for micro-batches of `micro_batch` frames (any caller batch is processed in
  * such slices).  Must precede the first forward. */
 int egn_plan(egn_ctx* ctx, int micro_batch);
@@ -127,6 +133,7 @@ typedef struct egn_info_t {
   int tensor_core_path;      /* 1 = tcgen05 kernel, 0 = SIMT companion (EGN_CONV=simt, debugging only) */
   long long workspace_bytes; /* device memory held by the context so far */
   long long activation_bytes_unshared; /* what the activation planes would take without liveness sharing (engine.cuh commit_acts) */
+  long long shared_pool_bytes; /* size of the per-device activation pool this context draws from (egn_share_workspace), not part of workspace_bytes; 0 = own arena */
   int lowered_layers;        /* convolution layers that run below the parity precision: fewer products than products_per_mac (EGN_PRODUCTS probe
                               * knob) or InstanceNorm folded into per-frame weights (EGN_IN_FOLD experiment); 0 in the parity configuration */
 } egn_info_t;

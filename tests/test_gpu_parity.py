@@ -617,6 +617,33 @@ def test_workspace_is_liveness_shared(env):
     assert (egn.get_predictions(c[0], m2) == egn.get_predictions(a[0], m)).float().mean().item() > 0.9999
 
 
+def test_shared_workspace_pool_between_the_two_modules(env):
+    """egn_share_workspace: the BDCN context lends its (dead) buffers to the ESF-Net - alternating forwards of the two
+    modules through ONE pool give the bits of separate arenas."""
+    egn, dev = env["egn"], env["dev"]
+    x, e_ref = env["img"].to(dev), env["edge_ref"].to(dev)
+    m0, st, esd = _model(env, "baseline_edge", mb=24)
+    with torch.no_grad():
+        ref = m0(x, e_ref, None, None, None, None, None, torch.zeros(2, 4, device=dev), 0, 0)
+    egn.share_workspace(True)
+    try:
+        em = egn.BDCN(); em.load_state_dict(env["bsd"]); em = em.cuda().eval(); em.micro_batch = 24
+        m, _, _ = _model(env, "baseline_edge", mb=24)
+        outs = []
+        with torch.no_grad():
+            for _ in range(2):
+                edge = em.edge(x)
+                outs.append((edge, m(x, e_ref, None, None, None, None, None, torch.zeros(2, 4, device=dev), 0, 0)))
+    finally:
+        egn.share_workspace(False)
+    for edge, o in outs:
+        np.testing.assert_allclose(edge.cpu().numpy(), env["edge_ref"].numpy(), atol=5e-4)
+        assert torch.equal(o[0], ref[0]) and torch.equal(o[4], ref[4])
+    bi, mi = em.context(dev).info(), m.context(dev).info()
+    assert bi["shared_pool_bytes"] > 0 and bi["shared_pool_bytes"] == mi["shared_pool_bytes"]
+    assert m0.context(dev).info()["shared_pool_bytes"] == 0
+
+
 def test_api_leaves_the_callers_device_alone(env):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
