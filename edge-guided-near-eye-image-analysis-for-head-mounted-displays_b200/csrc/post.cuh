@@ -277,92 +277,137 @@ __device__ inline void ell_transform(const double* p, double sx, double sy, doub
   ell_mat2param(m, out);
 }
 
+#ifndef REFINE_THREADS
 #define REFINE_THREADS 512
+#endif
+#ifndef REFINE_CLUSTER
 #define REFINE_CLUSTER 8     // CTAs (SMs) that raster one ellipse together
+#endif
 
-// Shared state of one refinement: three rotating (intersection, area) counter sets - only the ones
-// in the cluster's rank-0 CTA are used - so one cluster barrier per IoU evaluation suffices: set
-// (k+1) % 3 is cleared by rank 0 at the start of evaluation k, after every CTA has passed the barrier
-// of evaluation k-1 and therefore finished reading it (it was last used by evaluation k-2).
+// Shared state of one refinement: three rotating sets of (intersection, area) counters for up to three candidate
+// ellipses - only the ones in the cluster's rank-0 CTA are used - so one cluster barrier per raster pass suffices:
+// set (k+1) % 3 is cleared by rank 0 at the start of pass k, after every CTA has passed the barrier of pass k-1 and
+// therefore finished reading it (it was last used by pass k-2).
+#define REFINE_CAND 3
 struct RefineShared {
-  int cnt[3][2];
-  int local[2];
-  float e[4], c, s;
-  int box[4];
+  int cnt[3][REFINE_CAND][2];
+  int local[REFINE_CAND][2];
+  float e[REFINE_CAND][4], c[REFINE_CAND], s[REFINE_CAND];
+  int box[REFINE_CAND][4];
 };
 
-// IoU of the class mask against the raster of a pixel-space ellipse whose angle is in degrees
-// (utils.py:176-204 with nor=False, angle_nor=True; float32 raster arithmetic like the reference).
-// The REFINE_CLUSTER CTAs of a thread-block cluster split the rows; the integer counts are reduced
-// through distributed shared memory, so the score is identical in every CTA and bit-identical to a
-// whole-frame raster.
-__device__ float ell_iou_cluster(const uint8_t* __restrict__ seg, int cls, int seg_count, const double* center,
-                                 const double* abt, RefineShared* sh, int& eval) {
+template <int NC>
+__device__ __forceinline__ void ell_raster(const uint8_t* __restrict__ seg, int cls, RefineShared* sh, int rank,
+                                           int bx0, int bx1, int by0, int by1) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float ex[NC], ey[NC], ea[NC], eb[NC], cc[NC], ss[NC];
+  int inter[NC], area[NC];
+#pragma unroll
+  for (int q = 0; q < NC; ++q) {
+    ex[q] = sh->e[q][0]; ey[q] = sh->e[q][1]; ea[q] = sh->e[q][2]; eb[q] = sh->e[q][3]; cc[q] = sh->c[q]; ss[q] = sh->s[q];
+    inter[q] = 0; area[q] = 0;
+  }
+  // one image row per warp at a time, rows interleaved over the cluster's CTAs
+  for (int y = by0 + rank * (REFINE_THREADS / 32) + warp; y < by1; y += REFINE_CLUSTER * (REFINE_THREADS / 32)) {
+    const float my = linspace_m11(y, EGN_H);
+    const uint8_t* row = seg + y * EGN_W;
+    float dys[NC], dyc[NC];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) { dys[q] = __fmul_rn(my - ey[q], ss[q]); dyc[q] = __fmul_rn(my - ey[q], cc[q]); }
+    for (int x = bx0 + lane; x < bx1; x += 32) {
+      const float mx = linspace_m11(x, EGN_W);
+      const int hit = row[x] == cls;
+#pragma unroll
+      for (int q = 0; q < NC; ++q) {
+        const float X = __fadd_rn(__fmul_rn(mx - ex[q], cc[q]), dys[q]);
+        const float Y = __fadd_rn(__fmul_rn(-(mx - ex[q]), ss[q]), dyc[q]);
+        const float qx = X / ea[q], qy = Y / eb[q];
+        const float wt = __fadd_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)), -1.0f);
+        if (wt <= 0.f) { ++area[q]; inter[q] += hit; }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NC; ++q) {
+    for (int o = 16; o > 0; o >>= 1) {
+      inter[q] += __shfl_xor_sync(0xffffffffu, inter[q], o);
+      area[q] += __shfl_xor_sync(0xffffffffu, area[q], o);
+    }
+    if (lane == 0 && (inter[q] | area[q])) { atomicAdd(&sh->local[q][0], inter[q]); atomicAdd(&sh->local[q][1], area[q]); }
+  }
+}
+
+// IoU of the class mask against the rasters of up to three pixel-space ellipses (common centre, (a, b, angle in
+// degrees) each) in ONE pass over the pixels (utils.py:176-204 with nor=False, angle_nor=True; float32 raster
+// arithmetic like the reference, identical per candidate to a raster of its own).  The coordinate descent of
+// utils.py:450-486 evaluates its candidates one after the other, but the two directions of a parameter do not
+// depend on each other (the running best score only changes at the end of an iteration), and neither do the
+// end-of-iteration score and the first candidates of the next iteration - so they share a pass, and the number of
+// sequential passes (each a cluster barrier, a block barrier and a serial double-precision conic transform) drops
+// from up to 7 to 3 per iteration.  The REFINE_CLUSTER CTAs of a thread-block cluster split the rows; the integer
+// counts are reduced through distributed shared memory, so every score is identical in every CTA and bit-identical
+// to a whole-frame raster.
+__device__ void ell_iou_multi(const uint8_t* __restrict__ seg, int cls, int seg_count, const double* center,
+                              const double (*abt)[3], int ncand, RefineShared* sh, int& pass, float* score) {
   cg::cluster_group cl = cg::this_cluster();
   const int rank = (int)cl.block_rank();
-  const int k = eval % 3;
-  ++eval;
-  if (threadIdx.x == 0) {
-    double p[5] = {center[0], center[1], abt[0], abt[1], abt[2] / 180.0 * 3.14159};
+  const int k = pass % 3;
+  ++pass;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0 && warp < ncand) {
+    // one thread per candidate: the conic transform is serial double-precision work
+    const int q = warp;
+    double p[5] = {center[0], center[1], abt[q][0], abt[q][1], abt[q][2] / 180.0 * 3.14159};
     double o[5];
     ell_transform(p, 2.0 / EGN_W, 2.0 / EGN_H, -1.0, -1.0, o);
-    sh->e[0] = (float)o[0]; sh->e[1] = (float)o[1]; sh->e[2] = (float)o[2]; sh->e[3] = (float)o[3];
+    sh->e[q][0] = (float)o[0]; sh->e[q][1] = (float)o[1]; sh->e[q][2] = (float)o[2]; sh->e[q][3] = (float)o[3];
     // cos / sin are taken in double by the reference and then used as python floats
-    sh->c = (float)cos(o[4]); sh->s = (float)sin(o[4]);
-    sh->local[0] = 0; sh->local[1] = 0;
-    if (rank == 0) { sh->cnt[(k + 1) % 3][0] = 0; sh->cnt[(k + 1) % 3][1] = 0; }
+    sh->c[q] = (float)cos(o[4]); sh->s[q] = (float)sin(o[4]);
+    sh->local[q][0] = 0; sh->local[q][1] = 0;
+    if (rank == 0 && q == 0)                       // the next pass may carry more candidates than this one: clear them all
+      for (int z = 0; z < REFINE_CAND; ++z) { sh->cnt[(k + 1) % 3][z][0] = 0; sh->cnt[(k + 1) % 3][z][1] = 0; }
     // Only pixels inside the ellipse count (area, intersection), so the raster is restricted to a
     // conservative pixel-space bounding box: centre +- (1.01 * max(|a|, |b|) + 3) - the meshgrid maps
     // pixel x to x * W / (W - 1) in the ellipse's pixel frame, a stretch below 0.5 %.  Non-finite or
     // huge parameters fall back to the whole frame, which is what the reference rasterises.
     int bx0 = 0, bx1 = EGN_W, by0 = 0, by1 = EGN_H;
-    const double r = 1.01 * fmax(fabs(abt[0]), fabs(abt[1])) + 3.0;
+    const double r = 1.01 * fmax(fabs(abt[q][0]), fabs(abt[q][1])) + 3.0;
     if (r < 1.0e6 && fabs(center[0]) < 1.0e6 && fabs(center[1]) < 1.0e6) {   // false for NaN / inf
       bx0 = max(0, min(EGN_W, (int)floor(center[0] - r))); bx1 = max(bx0, min(EGN_W, (int)ceil(center[0] + r) + 1));
       by0 = max(0, min(EGN_H, (int)floor(center[1] - r))); by1 = max(by0, min(EGN_H, (int)ceil(center[1] + r) + 1));
     }
-    sh->box[0] = bx0; sh->box[1] = bx1; sh->box[2] = by0; sh->box[3] = by1;
+    sh->box[q][0] = bx0; sh->box[q][1] = bx1; sh->box[q][2] = by0; sh->box[q][3] = by1;
   }
   __syncthreads();
-  const float ex = sh->e[0], ey = sh->e[1], ea = sh->e[2], eb = sh->e[3], c = sh->c, s = sh->s;
-  const int bx0 = sh->box[0], bx1 = sh->box[1], by0 = sh->box[2], by1 = sh->box[3];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int inter = 0, area = 0;
-  // one image row per warp at a time, rows interleaved over the cluster's CTAs
-  for (int y = by0 + rank * (REFINE_THREADS / 32) + warp; y < by1; y += REFINE_CLUSTER * (REFINE_THREADS / 32)) {
-    const float my = linspace_m11(y, EGN_H);
-    const float dys = __fmul_rn(my - ey, s), dyc = __fmul_rn(my - ey, c);
-    const uint8_t* row = seg + y * EGN_W;
-    for (int x = bx0 + lane; x < bx1; x += 32) {
-      const float mx = linspace_m11(x, EGN_W);
-      const float X = __fadd_rn(__fmul_rn(mx - ex, c), dys);
-      const float Y = __fadd_rn(__fmul_rn(-(mx - ex), s), dyc);
-      const float qx = X / ea, qy = Y / eb;
-      const float wt = __fadd_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)), -1.0f);
-      if (wt <= 0.f) { ++area; inter += (row[x] == cls); }
-    }
+  // union of the candidates' boxes (outside its own box a candidate has no pixel inside the ellipse)
+  int bx0 = sh->box[0][0], bx1 = sh->box[0][1], by0 = sh->box[0][2], by1 = sh->box[0][3];
+  for (int q = 1; q < ncand; ++q) {
+    bx0 = min(bx0, sh->box[q][0]); bx1 = max(bx1, sh->box[q][1]);
+    by0 = min(by0, sh->box[q][2]); by1 = max(by1, sh->box[q][3]);
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    inter += __shfl_xor_sync(0xffffffffu, inter, o);
-    area += __shfl_xor_sync(0xffffffffu, area, o);
-  }
-  if (lane == 0 && (inter | area)) { atomicAdd(&sh->local[0], inter); atomicAdd(&sh->local[1], area); }
+  // the raster loop is specialised on the number of candidates (a runtime count costs the single-candidate passes
+  // of full batches ~7 %)
+  if (ncand == 1) ell_raster<1>(seg, cls, sh, rank, bx0, bx1, by0, by1);
+  else if (ncand == 2) ell_raster<2>(seg, cls, sh, rank, bx0, bx1, by0, by1);
+  else ell_raster<3>(seg, cls, sh, rank, bx0, bx1, by0, by1);
   __syncthreads();
   RefineShared* r0 = cl.map_shared_rank(sh, 0);
-  if (threadIdx.x == 0 && (sh->local[0] | sh->local[1])) {
-    atomicAdd(&r0->cnt[k][0], sh->local[0]);
-    atomicAdd(&r0->cnt[k][1], sh->local[1]);
+  if ((int)threadIdx.x < ncand && (sh->local[threadIdx.x][0] | sh->local[threadIdx.x][1])) {
+    atomicAdd(&r0->cnt[k][threadIdx.x][0], sh->local[threadIdx.x][0]);
+    atomicAdd(&r0->cnt[k][threadIdx.x][1], sh->local[threadIdx.x][1]);
   }
   cl.sync();
-  const float I = (float)r0->cnt[k][0], A = (float)r0->cnt[k][1];
-  return I / (((float)seg_count + A) - I);
+  for (int q = 0; q < ncand; ++q) {
+    const float I = (float)r0->cnt[k][q][0], A = (float)r0->cnt[k][q][1];
+    score[q] = I / (((float)seg_count + A) - I);
+  }
 }
 
 // ell_norm: [B][2][5] normalised (iris, pupil) ellipses (elPred); out: [B][2][5] refined pixel ellipses
 // (cx, cy, a, b, theta_rad), iris first.  grid = (REFINE_CLUSTER, 2, B), one cluster per ellipse.
-__global__ void __cluster_dims__(REFINE_CLUSTER, 1, 1) __launch_bounds__(REFINE_THREADS)
+__global__ void __cluster_dims__(REFINE_CLUSTER, 1, 1) __launch_bounds__(REFINE_THREADS, 2)
 ellipse_refine_kernel(const uint8_t* __restrict__ argmax, const float* __restrict__ ell_norm,
-                      double* __restrict__ out, int do_refine) {
+                      double* __restrict__ out, int do_refine, int speculate) {
   cg::cluster_group cl = cg::this_cluster();
   const int which = blockIdx.y, n = blockIdx.z;
   const int cls = which == 0 ? 1 : 2;             // iris mask == 1, pupil mask == 2 (evaluate.py:148-151)
@@ -372,7 +417,8 @@ ellipse_refine_kernel(const uint8_t* __restrict__ argmax, const float* __restric
   __shared__ double px[5];
   if (threadIdx.x == 0) {
     sh_seg = 0;
-    for (int i = 0; i < 3; ++i) { sh.cnt[i][0] = 0; sh.cnt[i][1] = 0; }
+    for (int i = 0; i < 3; ++i)
+      for (int q = 0; q < REFINE_CAND; ++q) { sh.cnt[i][q][0] = 0; sh.cnt[i][q][1] = 0; }
     double p[5];
     for (int i = 0; i < 5; ++i) p[i] = (double)ell_norm[((size_t)n * 2 + which) * 5 + i];
     ell_transform(p, EGN_W / 2.0, EGN_H / 2.0, EGN_W / 2.0, EGN_H / 2.0, px);
@@ -394,24 +440,63 @@ ellipse_refine_kernel(const uint8_t* __restrict__ argmax, const float* __restric
   double center[2] = {px[0], px[1]};
   double now[3] = {px[2], px[3], px[4] * 180.0 / 3.14159};
   if (do_refine) {
-    int eval = 0;
-    float rt = ell_iou_cluster(seg, cls, seg_count, center, now, &sh, eval);
+    // utils.py:450-486:  for tt in 40: flag = False; for j in 3: { now[j] -= d[j]; if iou(now) > rt: flag = True; continue;
+    //   now[j] += 2 d[j]; if iou(now) > rt: flag = True; continue;  now[j] -= d[j]; d[j] *= 0.8 }
+    //   sc = iou(now); if sc > rt: rt = sc; if not flag: break
+    // The end-of-iteration score only matters when another iteration follows (the result is `now`), so it is
+    // evaluated together with that iteration's first candidate pair.
+    int pass = 0;
+    double cand[REFINE_CAND][3];
+    float sc[REFINE_CAND];
+    for (int i = 0; i < 3; ++i) cand[0][i] = now[i];
+    ell_iou_multi(seg, cls, seg_count, center, cand, 1, &sh, pass, sc);
+    float rt = sc[0];
     double d[3] = {1.0, 1.0, 1.0};
-    for (int tt = 0; tt < 40; ++tt) {
-      bool flag = false;
-      for (int j = 0; j < 3; ++j) {
-        now[j] -= d[j];
-        float sc = ell_iou_cluster(seg, cls, seg_count, center, now, &sh, eval);
-        if (sc > rt) { flag = true; continue; }
-        now[j] += 2.0 * d[j];
-        sc = ell_iou_cluster(seg, cls, seg_count, center, now, &sh, eval);
-        if (sc > rt) { flag = true; continue; }
-        now[j] -= d[j];
-        d[j] *= 0.8;
+    if (speculate) {
+      // few ellipses (streaming batches: the GPU is mostly idle): both directions per pass, closing score merged
+      for (int tt = 0; tt < 40; ++tt) {
+        bool flag = false;
+        for (int j = 0; j < 3; ++j) {
+          const double minus = now[j] - d[j];
+          const double plus = minus + 2.0 * d[j];
+          int nc = 0, first = 0;
+          if (j == 0 && tt > 0) {                    // the previous iteration's closing score
+            for (int i = 0; i < 3; ++i) cand[nc][i] = now[i];
+            ++nc; first = 1;
+          }
+          for (int i = 0; i < 3; ++i) { cand[nc][i] = now[i]; cand[nc + 1][i] = now[i]; }
+          cand[nc][j] = minus; cand[nc + 1][j] = plus;
+          nc += 2;
+          ell_iou_multi(seg, cls, seg_count, center, cand, nc, &sh, pass, sc);
+          if (first && sc[0] > rt) rt = sc[0];
+          if (sc[first] > rt) { now[j] = minus; flag = true; continue; }
+          if (sc[first + 1] > rt) { now[j] = plus; flag = true; continue; }
+          now[j] = plus - d[j];
+          d[j] *= 0.8;
+        }
+        if (!flag) break;
       }
-      const float sc = ell_iou_cluster(seg, cls, seg_count, center, now, &sh, eval);
-      if (sc > rt) rt = sc;
-      if (!flag) break;
+    } else {
+      // many ellipses (the GPU is full): the reference's own order, one candidate per pass, no speculative rasters
+      for (int tt = 0; tt < 40; ++tt) {
+        bool flag = false;
+        for (int j = 0; j < 3; ++j) {
+          now[j] -= d[j];
+          for (int i = 0; i < 3; ++i) cand[0][i] = now[i];
+          ell_iou_multi(seg, cls, seg_count, center, cand, 1, &sh, pass, sc);
+          if (sc[0] > rt) { flag = true; continue; }
+          now[j] += 2.0 * d[j];
+          for (int i = 0; i < 3; ++i) cand[0][i] = now[i];
+          ell_iou_multi(seg, cls, seg_count, center, cand, 1, &sh, pass, sc);
+          if (sc[0] > rt) { flag = true; continue; }
+          now[j] -= d[j];
+          d[j] *= 0.8;
+        }
+        if (!flag || tt == 39) break;              // the closing score only matters when another iteration follows
+        for (int i = 0; i < 3; ++i) cand[0][i] = now[i];
+        ell_iou_multi(seg, cls, seg_count, center, cand, 1, &sh, pass, sc);
+        if (sc[0] > rt) rt = sc[0];
+      }
     }
   }
   if (threadIdx.x == 0 && cl.block_rank() == 0) {

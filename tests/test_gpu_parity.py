@@ -229,6 +229,14 @@ def test_ellipse_transform_and_refinement(env):
                 assert env["graph"].ell_iou(m, deg(got)) >= env["graph"].ell_iou(m, deg(ref)) - 0.01
                 np.testing.assert_allclose(got[:2], ref[:2], atol=0.05)
     assert np.isfinite(out[:k]).all()
+    # both schedules of the search (two directions per raster pass, and the reference's one candidate per pass)
+    # walk the same path: same bits
+    os.environ["EGN_REFINE_SPECULATE"] = "0"
+    try:
+        seq = ctx.ellipse_refine(torch.from_numpy(seg).to(dev), torch.from_numpy(ell), refine=True).cpu().numpy()
+    finally:
+        del os.environ["EGN_REFINE_SPECULATE"]
+    np.testing.assert_array_equal(seq, out)
     # degenerate pupil: NaN objective, parameters come back unrefined
     np.testing.assert_allclose(out[k, 1], env["graph"].ellipse_norm_to_px(ell[k, 1].astype(np.float64)), rtol=1e-9)
     print("ellipse refinement: worst relative deviation of (a, b, theta) from the oracle %.2e" % worst)
