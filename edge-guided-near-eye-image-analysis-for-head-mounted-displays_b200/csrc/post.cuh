@@ -225,39 +225,48 @@ __global__ void metrics_finish_kernel(const int* __restrict__ counts, const floa
 // and the IoU coordinate descent of utils.py:450-486, one block per ellipse, fully on device.
 struct Mat3 { double m[3][3]; };
 
-__device__ inline Mat3 mat_mul(const Mat3& a, const Mat3& b) {
+// (fully unrolled and inlined: with runtime loop indices the 3x3 matrices live in local memory, and the conic
+//  transform - serial double-precision work on one thread per candidate - sits on the critical path of every
+//  raster pass of the refinement; the order of the operations, hence every bit of the result, is unchanged)
+__device__ __forceinline__ Mat3 mat_mul(const Mat3& a, const Mat3& b) {
   Mat3 r;
+#pragma unroll
   for (int i = 0; i < 3; ++i)
+#pragma unroll
     for (int j = 0; j < 3; ++j) {
       double s = 0;
+#pragma unroll
       for (int k = 0; k < 3; ++k) s += a.m[i][k] * b.m[k][j];
       r.m[i][j] = s;
     }
   return r;
 }
-__device__ inline Mat3 mat_t(const Mat3& a) {
+__device__ __forceinline__ Mat3 mat_t(const Mat3& a) {
   Mat3 r;
-  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[i][j] = a.m[j][i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r.m[i][j] = a.m[j][i];
   return r;
 }
-__device__ inline Mat3 rot2d(double t) {
+__device__ __forceinline__ Mat3 rot2d(double t) {
   const double c = cos(t), s = sin(t);
   Mat3 r = {{{c, -s, 0}, {s, c, 0}, {0, 0, 1}}};
   return r;
 }
-__device__ inline Mat3 trans2d(double x, double y) {
+__device__ __forceinline__ Mat3 trans2d(double x, double y) {
   Mat3 r = {{{1, 0, x}, {0, 1, y}, {0, 0, 1}}};
   return r;
 }
 
 // conic of (cx, cy, a, b, theta)
-__device__ inline Mat3 ell_param2mat(const double* p) {
+__device__ __forceinline__ Mat3 ell_param2mat(const double* p) {
   const Mat3 Hr = rot2d(-p[4]), Ht = trans2d(-p[0], -p[1]);
   Mat3 Q = {{{1.0 / (p[2] * p[2]), 0, 0}, {0, 1.0 / (p[3] * p[3]), 0}, {0, 0, -1}}};
   return mat_mul(mat_mul(mat_mul(mat_mul(mat_t(Ht), mat_t(Hr)), Q), Hr), Ht);
 }
 
-__device__ inline void ell_mat2param(const Mat3& m, double* out) {
+__device__ __forceinline__ void ell_mat2param(const Mat3& m, double* out) {
   const double a = m.m[0][0], b = 2 * m.m[0][1], c = m.m[1][1], d = 2 * m.m[0][2], e = 2 * m.m[1][2];
   double th;
   if (fabs(b) <= 1e-40 && a <= c) th = 0.0;
@@ -271,7 +280,7 @@ __device__ inline void ell_mat2param(const Mat3& m, double* out) {
 }
 
 // transform with a diagonal-plus-shift homography H = [[sx,0,tx],[0,sy,ty],[0,0,1]]
-__device__ inline void ell_transform(const double* p, double sx, double sy, double tx, double ty, double* out) {
+__device__ __forceinline__ void ell_transform(const double* p, double sx, double sy, double tx, double ty, double* out) {
   Mat3 Hi = {{{1.0 / sx, 0, -tx / sx}, {0, 1.0 / sy, -ty / sy}, {0, 0, 1}}};
   const Mat3 m = mat_mul(mat_mul(mat_t(Hi), ell_param2mat(p)), Hi);
   ell_mat2param(m, out);
@@ -296,8 +305,11 @@ struct RefineShared {
   int box[REFINE_CAND][4];
 };
 
+#define REFINE_ROWS (REFINE_CLUSTER * (REFINE_THREADS / 32))                 // rows one sweep of the cluster covers
+#define REFINE_SWEEPS ((EGN_H + REFINE_ROWS - 1) / REFINE_ROWS)
+
 template <int NC>
-__device__ __forceinline__ void ell_raster(const uint8_t* __restrict__ seg, int cls, RefineShared* sh, int rank,
+__device__ __forceinline__ void ell_raster(const uint8_t (*smask)[REFINE_THREADS / 32][EGN_W], int cls, RefineShared* sh, int rank,
                                            int bx0, int bx1, int by0, int by1) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float ex[NC], ey[NC], ea[NC], eb[NC], cc[NC], ss[NC];
@@ -307,10 +319,14 @@ __device__ __forceinline__ void ell_raster(const uint8_t* __restrict__ seg, int 
     ex[q] = sh->e[q][0]; ey[q] = sh->e[q][1]; ea[q] = sh->e[q][2]; eb[q] = sh->e[q][3]; cc[q] = sh->c[q]; ss[q] = sh->s[q];
     inter[q] = 0; area[q] = 0;
   }
-  // one image row per warp at a time, rows interleaved over the cluster's CTAs
-  for (int y = by0 + rank * (REFINE_THREADS / 32) + warp; y < by1; y += REFINE_CLUSTER * (REFINE_THREADS / 32)) {
+  // one image row per warp at a time; row y belongs to warp (y % REFINE_ROWS) of the cluster for the whole launch, and
+  // its mask bytes were copied to shared memory once (every pass of the search used to wait for them from L2)
+#pragma unroll
+  for (int sw = 0; sw < REFINE_SWEEPS; ++sw) {
+    const int y = sw * REFINE_ROWS + rank * (REFINE_THREADS / 32) + warp;
+    if (y < by0 || y >= by1) continue;
     const float my = linspace_m11(y, EGN_H);
-    const uint8_t* row = seg + y * EGN_W;
+    const uint8_t* row = smask[sw][warp];
     float dys[NC], dyc[NC];
 #pragma unroll
     for (int q = 0; q < NC; ++q) { dys[q] = __fmul_rn(my - ey[q], ss[q]); dyc[q] = __fmul_rn(my - ey[q], cc[q]); }
@@ -347,7 +363,7 @@ __device__ __forceinline__ void ell_raster(const uint8_t* __restrict__ seg, int 
 // from up to 7 to 3 per iteration.  The REFINE_CLUSTER CTAs of a thread-block cluster split the rows; the integer
 // counts are reduced through distributed shared memory, so every score is identical in every CTA and bit-identical
 // to a whole-frame raster.
-__device__ void ell_iou_multi(const uint8_t* __restrict__ seg, int cls, int seg_count, const double* center,
+__device__ void ell_iou_multi(const uint8_t (*smask)[REFINE_THREADS / 32][EGN_W], int cls, int seg_count, const double* center,
                               const double (*abt)[3], int ncand, RefineShared* sh, int& pass, float* score) {
   cg::cluster_group cl = cg::this_cluster();
   const int rank = (int)cl.block_rank();
@@ -387,9 +403,9 @@ __device__ void ell_iou_multi(const uint8_t* __restrict__ seg, int cls, int seg_
   }
   // the raster loop is specialised on the number of candidates (a runtime count costs the single-candidate passes
   // of full batches ~7 %)
-  if (ncand == 1) ell_raster<1>(seg, cls, sh, rank, bx0, bx1, by0, by1);
-  else if (ncand == 2) ell_raster<2>(seg, cls, sh, rank, bx0, bx1, by0, by1);
-  else ell_raster<3>(seg, cls, sh, rank, bx0, bx1, by0, by1);
+  if (ncand == 1) ell_raster<1>(smask, cls, sh, rank, bx0, bx1, by0, by1);
+  else if (ncand == 2) ell_raster<2>(smask, cls, sh, rank, bx0, bx1, by0, by1);
+  else ell_raster<3>(smask, cls, sh, rank, bx0, bx1, by0, by1);
   __syncthreads();
   RefineShared* r0 = cl.map_shared_rank(sh, 0);
   if ((int)threadIdx.x < ncand && (sh->local[threadIdx.x][0] | sh->local[threadIdx.x][1])) {
@@ -405,7 +421,7 @@ __device__ void ell_iou_multi(const uint8_t* __restrict__ seg, int cls, int seg_
 
 // ell_norm: [B][2][5] normalised (iris, pupil) ellipses (elPred); out: [B][2][5] refined pixel ellipses
 // (cx, cy, a, b, theta_rad), iris first.  grid = (REFINE_CLUSTER, 2, B), one cluster per ellipse.
-__global__ void __cluster_dims__(REFINE_CLUSTER, 1, 1) __launch_bounds__(REFINE_THREADS, 2)
+__global__ void __cluster_dims__(REFINE_CLUSTER, 1, 1) __launch_bounds__(REFINE_THREADS, REFINE_THREADS <= 512 ? 2 : 1)
 ellipse_refine_kernel(const uint8_t* __restrict__ argmax, const float* __restrict__ ell_norm,
                       double* __restrict__ out, int do_refine, int speculate) {
   cg::cluster_group cl = cg::this_cluster();
@@ -415,6 +431,19 @@ ellipse_refine_kernel(const uint8_t* __restrict__ argmax, const float* __restric
   __shared__ RefineShared sh;
   __shared__ int sh_seg;
   __shared__ double px[5];
+  __shared__ __align__(16) uint8_t smask[REFINE_SWEEPS][REFINE_THREADS / 32][EGN_W];   // this CTA's rows of the class map
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cl.block_rank();
+    for (int sw = 0; sw < REFINE_SWEEPS; ++sw) {
+      const int y = sw * REFINE_ROWS + rank * (REFINE_THREADS / 32) + warp;
+      if (y < EGN_H) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(seg + (size_t)y * EGN_W);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smask[sw][warp]);
+        for (int i = lane; i < EGN_W / 4; i += 32) dst[i] = __ldg(src + i);
+      }
+    }
+  }
   if (threadIdx.x == 0) {
     sh_seg = 0;
     for (int i = 0; i < 3; ++i)
@@ -449,7 +478,7 @@ ellipse_refine_kernel(const uint8_t* __restrict__ argmax, const float* __restric
     double cand[REFINE_CAND][3];
     float sc[REFINE_CAND];
     for (int i = 0; i < 3; ++i) cand[0][i] = now[i];
-    ell_iou_multi(seg, cls, seg_count, center, cand, 1, &sh, pass, sc);
+    ell_iou_multi(smask, cls, seg_count, center, cand, 1, &sh, pass, sc);
     float rt = sc[0];
     double d[3] = {1.0, 1.0, 1.0};
     if (speculate) {
@@ -467,7 +496,7 @@ ellipse_refine_kernel(const uint8_t* __restrict__ argmax, const float* __restric
           for (int i = 0; i < 3; ++i) { cand[nc][i] = now[i]; cand[nc + 1][i] = now[i]; }
           cand[nc][j] = minus; cand[nc + 1][j] = plus;
           nc += 2;
-          ell_iou_multi(seg, cls, seg_count, center, cand, nc, &sh, pass, sc);
+          ell_iou_multi(smask, cls, seg_count, center, cand, nc, &sh, pass, sc);
           if (first && sc[0] > rt) rt = sc[0];
           if (sc[first] > rt) { now[j] = minus; flag = true; continue; }
           if (sc[first + 1] > rt) { now[j] = plus; flag = true; continue; }
@@ -483,18 +512,18 @@ ellipse_refine_kernel(const uint8_t* __restrict__ argmax, const float* __restric
         for (int j = 0; j < 3; ++j) {
           now[j] -= d[j];
           for (int i = 0; i < 3; ++i) cand[0][i] = now[i];
-          ell_iou_multi(seg, cls, seg_count, center, cand, 1, &sh, pass, sc);
+          ell_iou_multi(smask, cls, seg_count, center, cand, 1, &sh, pass, sc);
           if (sc[0] > rt) { flag = true; continue; }
           now[j] += 2.0 * d[j];
           for (int i = 0; i < 3; ++i) cand[0][i] = now[i];
-          ell_iou_multi(seg, cls, seg_count, center, cand, 1, &sh, pass, sc);
+          ell_iou_multi(smask, cls, seg_count, center, cand, 1, &sh, pass, sc);
           if (sc[0] > rt) { flag = true; continue; }
           now[j] -= d[j];
           d[j] *= 0.8;
         }
         if (!flag || tt == 39) break;              // the closing score only matters when another iteration follows
         for (int i = 0; i < 3; ++i) cand[0][i] = now[i];
-        ell_iou_multi(seg, cls, seg_count, center, cand, 1, &sh, pass, sc);
+        ell_iou_multi(smask, cls, seg_count, center, cand, 1, &sh, pass, sc);
         if (sc[0] > rt) rt = sc[0];
       }
     }
